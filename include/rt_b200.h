@@ -155,6 +155,8 @@ typedef struct rt_stats {
     float ms_render;       /* device time, first kernel .. resolved RGB8 in device memory */
     float ms_total;        /* call wall time including copies                            */
     uint32_t kernel_launches;
+    uint32_t megakernel_launches; /* render_kernel launches among kernel_launches            */
+    float ms_megakernel;          /* summed device time of the render_kernel launches alone   */
     uint32_t reserved;
 } rt_stats;
 
@@ -172,6 +174,10 @@ int rt_device_count(void);
  * depth-first order, and uploads nodes / spheres / materials / texels once. */
 int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out);
 void rt_scene_destroy(rt_scene *scene);
+/* Run this handle's kernels and copies on the caller's CUDA stream (a cudaStream_t; NULL restores
+ * the handle's own stream).  Lets a host framework order the render with its own work (e.g. an
+ * NCCL reduce of the accumulators) and time it with events on that stream. */
+int rt_scene_set_stream(rt_scene *scene, void *cuda_stream);
 
 /* Replaces the compute half of Camera.Render (camera.go:198-222): GetPixelColor for every pixel
  * (camera.go:254-263), gamma, clamp and quantise (vec3.go:141-166).  rgb_out receives
@@ -188,9 +194,10 @@ int rt_render(rt_scene *scene, const rt_camera *camera, const rt_render_opts *op
 int rt_render_accum_device(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts,
                            float *d_accum, rt_stats *stats);
 /* camera.go:261 + camera.go:212-214: scale by 1/total_spp, sqrt, clamp, *255.999, truncate.
- * d_accum: device sums; rgb_out: HOST buffer of width*height*3 bytes. */
+ * d_accum: device sums; rgb_out: HOST buffer of width*height*3 bytes.  Runs on cuda_stream (a
+ * cudaStream_t, NULL = the default stream) and returns after the copy has completed. */
 int rt_resolve_device(const float *d_accum, int32_t width, int32_t height, int32_t total_spp,
-                      int32_t device, uint8_t *rgb_out);
+                      int32_t device, void *cuda_stream, uint8_t *rgb_out);
 
 /* Parity hook with World.Hit semantics (hittables.go:55-72) on an arbitrary ray batch:
  * origins/dirs are n*3 float32 (host), interval (tmin, tmax) is open (bvh.go:18-20).
@@ -209,15 +216,20 @@ int rt_primary_rays(const rt_camera *camera, const rt_render_opts *opts, int64_t
 int rt_camera_from_options(const rt_camera_options *o, rt_camera *out);
 
 /* Introspection of the flattened device BVH (tests and the work-counting oracle).
- * Node i is 8 x 32-bit words: min.xyz, a, max.xyz, b.  Inner: a = index of the right child
- * (the left child is i+1), b = 0.  Leaf: a = first sphere slot, b = sphere count (>0).
- * slot_ids maps a sphere slot to its index in rt_scene_desc.spheres. */
+ * Node i is 8 x 32-bit words: min.xyz, ref, max.xyz, 0 — its own box and what it contains.
+ * ref of an inner node = index of the first of its two children (children are nodes ref and
+ * ref+1, siblings adjacent, parents before children: depth-first order); ref of a leaf =
+ * 0x80000000 | first_slot << 3 | (count-1), 1..8 spheres.  root_ref describes the root (whose
+ * box is not stored); 0xFFFFFFFF for an empty scene.  slot_ids maps a sphere slot to its index
+ * in rt_scene_desc.spheres. */
 typedef struct rt_bvh_info {
     uint64_t n_nodes;
     uint64_t n_slots;
     uint32_t max_depth;
     uint32_t in_shared_memory; /* 1 when the scene fits the per-CTA shared-memory staging path */
     float box_pad_min, box_pad_max;
+    uint32_t root_ref;
+    uint32_t reserved;
 } rt_bvh_info;
 int rt_scene_bvh_info(const rt_scene *scene, rt_bvh_info *out);
 int rt_scene_bvh_copy(const rt_scene *scene, uint32_t *nodes_out /* n_nodes*8 */,

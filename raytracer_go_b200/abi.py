@@ -73,13 +73,14 @@ class rt_render_opts(C.Structure):
 class rt_stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("box_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("hits", C.c_uint64), ("ms_render", C.c_float),
-                ("ms_total", C.c_float), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ms_total", C.c_float), ("kernel_launches", C.c_uint32),
+                ("megakernel_launches", C.c_uint32), ("ms_megakernel", C.c_float), ("reserved", C.c_uint32)]
 
 
 class rt_bvh_info(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_slots", C.c_uint64), ("max_depth", C.c_uint32),
                 ("in_shared_memory", C.c_uint32), ("box_pad_min", C.c_float),
-                ("box_pad_max", C.c_float)]
+                ("box_pad_max", C.c_float), ("root_ref", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/rt_b200.h declares.
@@ -89,13 +90,14 @@ PROTOTYPES = {
     "rt_device_count": (C.c_int, []),
     "rt_scene_create": (C.c_int, [C.POINTER(rt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]),
     "rt_scene_destroy": (None, [C.c_void_p]),
+    "rt_scene_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_opts),
                             C.c_void_p, C.c_void_p, C.POINTER(rt_stats)]),
     "rt_render_accum_device": (C.c_int, [C.c_void_p, C.POINTER(rt_camera),
                                          C.POINTER(rt_render_opts), C.c_void_p,
                                          C.POINTER(rt_stats)]),
     "rt_resolve_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                    C.c_void_p]),
+                                    C.c_void_p, C.c_void_p]),
     "rt_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                            C.c_void_p, C.c_void_p]),
     "rt_primary_rays": (C.c_int, [C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_int64,

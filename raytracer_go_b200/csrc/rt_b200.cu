@@ -1,0 +1,899 @@
+// rt_b200.cu — CUDA kernels (sm_100a) and the C ABI of librt_b200.so (include/rt_b200.h).
+//
+// Kernels
+//   render_kernel     persistent megakernel: one lane = one (pixel, sample) path at a time
+//                     (camera.go:254-299 + ray.go:32-54 + bvh.go:220-249 + hittables.go:96-132 +
+//                     materials.go), lanes regenerate from a warp-private chunk of the path index
+//                     space when their path ends; the scene (nodes, spheres, materials) is staged
+//                     once per CTA in shared memory when it fits, read with LDS.128.
+//   reduce_kernel     per pixel, adds the pass's per-sample radiances to the FP32 accumulator in
+//                     sample order — exactly the sequential `sample.Add(s)` of camera.go:256-260.
+//   resolve_kernel    camera.go:261 + vec3.go:141-166: 1/spp, sqrt, clamp, *255.999, truncate.
+//   trace_kernel      rt_trace parity hook: closest hit (object index, t) for a ray batch.
+//   primary_kernel    rt_primary_rays parity hook: Camera.GetRay on the device.
+//
+// Compiled with -fmad=false: see rt_math.h.  No tensor cores (not a contraction), no RT cores
+// (B200 has none).  There is no CPU path: every entry point that computes needs an sm_100 device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "bvh_build.h"
+#include "rt_math.h"
+#include "rt_rng.h"
+#include "rt_shade.h"
+#include "rt_trace.h"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA,     \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-side scene
+// ---------------------------------------------------------------------------------------------
+struct DevScene {
+    const F4 *nodes;
+    const F4 *sph;
+    const I2 *meta;
+    const F4 *mats;
+    const DevImage *images;
+    uint32_t root_ref, n_nodes, n_slots, n_mats;
+    uint32_t stack_depth; // entries per thread for the shared-memory stack
+};
+
+static size_t scene_smem_bytes(const DevScene &s) {
+    return (size_t)s.n_nodes * 32 + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 + (size_t)s.n_slots * 8;
+}
+
+#define RT_LOCAL_STACK 64
+
+// Stage the scene arrays in shared memory (LDG.128 -> STS.128), return the carved pointers.
+struct SmemScene {
+    const F4 *nodes, *sph, *mats;
+    const I2 *meta;
+    uint32_t *stack;
+};
+
+__device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned char *smem) {
+    F4 *nodes = reinterpret_cast<F4 *>(smem);
+    F4 *sph = nodes + 2 * (size_t)sc.n_nodes;
+    F4 *mats = sph + sc.n_slots;
+    I2 *meta = reinterpret_cast<I2 *>(mats + 2 * (size_t)sc.n_mats);
+    uint32_t *stack = reinterpret_cast<uint32_t *>(meta + sc.n_slots + (sc.n_slots & 1));
+    const uint4 *src;
+    uint4 *dst;
+    src = reinterpret_cast<const uint4 *>(sc.nodes), dst = reinterpret_cast<uint4 *>(nodes);
+    for (uint32_t i = threadIdx.x; i < 2 * sc.n_nodes; i += blockDim.x) dst[i] = __ldg(src + i);
+    src = reinterpret_cast<const uint4 *>(sc.sph), dst = reinterpret_cast<uint4 *>(sph);
+    for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) dst[i] = __ldg(src + i);
+    src = reinterpret_cast<const uint4 *>(sc.mats), dst = reinterpret_cast<uint4 *>(mats);
+    for (uint32_t i = threadIdx.x; i < 2 * sc.n_mats; i += blockDim.x) dst[i] = __ldg(src + i);
+    const uint2 *s2 = reinterpret_cast<const uint2 *>(sc.meta);
+    uint2 *d2 = reinterpret_cast<uint2 *>(meta);
+    for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) d2[i] = __ldg(s2 + i);
+    __syncthreads();
+    SmemScene r;
+    r.nodes = nodes, r.sph = sph, r.mats = mats, r.meta = meta, r.stack = stack;
+    return r;
+}
+
+static size_t smem_total_bytes(const DevScene &s, int block) {
+    size_t b = scene_smem_bytes(s) + ((s.n_slots & 1) ? 8 : 0);
+    return b + (size_t)s.stack_depth * block * 4;
+}
+
+// ---------------------------------------------------------------------------------------------
+// render megakernel
+// ---------------------------------------------------------------------------------------------
+struct RenderParams {
+    DevScene sc;
+    DevCamera cam;
+    uint64_t seed;
+    uint32_t pixel_begin;  // first pixel of this pass (row-major index)
+    uint32_t sample_begin; // global index of the first sample of this pass
+    uint32_t spp_pass;     // samples per pixel in this pass
+    uint32_t total_paths;  // n_pixels_pass * spp_pass
+    float4 *samples;       // [total_paths] radiance of path (pixel - pixel_begin) * spp_pass + k
+    unsigned int *counter; // next unclaimed path index
+    unsigned long long *stats; // rays, hits, box tests, sphere tests
+};
+
+#define RT_CHUNK 256u /* path indices a warp claims per atomic */
+
+template <int BLOCK, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(BLOCK) render_kernel(const __grid_constant__ RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats;
+    const I2 *meta = p.sc.meta;
+    uint32_t *stack_mem = nullptr;
+    if (SMEM) {
+        SmemScene s = stage_scene(p.sc, smem_raw);
+        nodes = s.nodes, sph = s.sph, mats = s.mats, meta = s.meta, stack_mem = s.stack;
+    }
+    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
+    Stack stack;
+    if constexpr (SMEM) {
+        stack.base = stack_mem + threadIdx.x;
+        stack.stride = BLOCK;
+    }
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t warp_next = 0, warp_end = 0;
+    bool exhausted = false;
+
+    bool alive = false;
+    uint32_t idx = 0;
+    int depth = 0;
+    V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1), rad = v3(0, 0, 0);
+    PathRng rng;
+    rng.init(0, 0, 0);
+    unsigned long long n_rays = 0, n_hits = 0;
+    WorkCounters wc;
+    wc.box_tests = wc.sphere_tests = 0;
+
+    for (;;) {
+        // ---- regeneration: dead lanes take the next path indices of the warp's chunk ----
+        const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+        if (dead) {
+            if (warp_next >= warp_end && !exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= p.total_paths) {
+                    exhausted = true;
+                } else {
+                    warp_next = base;
+                    warp_end = min(base + RT_CHUNK, p.total_paths);
+                }
+            }
+            const uint32_t avail = warp_end - warp_next;
+            const uint32_t rank = __popc(dead & lt_mask);
+            if (!alive && rank < avail) {
+                idx = warp_next + rank;
+                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                const uint32_t pixel = p.pixel_begin + pp;
+                const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+                rng.init(p.seed, pixel, p.sample_begin + k);
+                generate_ray(p.cam, rng, i, j, o, d);
+                thr = v3(1, 1, 1), rad = v3(0, 0, 0), depth = 0;
+                alive = true;
+            }
+            warp_next += min(avail, (uint32_t)__popc(dead));
+            if (exhausted && __ballot_sync(0xffffffffu, alive) == 0) break;
+        }
+        if (!alive) continue;
+
+        // ---- one path segment: ray.go:32-54 unrolled front to back ----
+        HitRec h;
+        trace_closest<Stack, COUNT>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc);
+        n_rays++;
+        bool done;
+        if (h.slot == RT_REF_NONE) {
+            rad = rad + thr * p.cam.background; // ray.go:53
+            done = true;
+        } else {
+            n_hits++;
+            const F4 s = sph[h.slot];
+            const int mi = meta[h.slot].y;
+            const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
+            V3 atten, emitted;
+            const bool scattered = shade_hit(m0, m1, p.sc.images, s, h.t, rng, o, d, atten, emitted);
+            rad = rad + thr * emitted; // ray.go:41,50
+            if (!scattered) {
+                done = true; // ray.go:44-46
+            } else {
+                thr = thr * atten; // ray.go:48
+                depth++;
+                done = depth >= p.cam.max_depth; // ray.go:33-35
+            }
+        }
+        if (done) {
+            p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
+            alive = false;
+        }
+    }
+
+    // ---- work counters: warp shuffle reduction, one atomic per warp ----
+    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
+#pragma unroll
+    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
+        unsigned long long x = v[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0 && x) atomicAdd(p.stats + q, x);
+    }
+}
+
+// accum[pixel] (+)= sum_k samples[(pixel - pixel_begin) * spp_pass + k], k ascending: the FP32
+// summation order of camera.go:255-260.  first_pass: start from zero instead of accum.
+__global__ void reduce_kernel(const float4 *__restrict__ samples, float *__restrict__ accum, uint32_t pixel_begin,
+                              uint32_t n_pixels, uint32_t spp_pass, int first_pass) {
+    const uint32_t pp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pp >= n_pixels) return;
+    float *a = accum + 3 * (size_t)(pixel_begin + pp);
+    V3 sum = first_pass ? v3(0, 0, 0) : v3(a[0], a[1], a[2]);
+    const float4 *s = samples + (size_t)pp * spp_pass;
+    for (uint32_t k = 0; k < spp_pass; k++) {
+        const float4 r = s[k];
+        sum = sum + v3(r.x, r.y, r.z);
+    }
+    a[0] = sum.x, a[1] = sum.y, a[2] = sum.z;
+}
+
+__global__ void resolve_kernel(const float *__restrict__ accum, uint8_t *__restrict__ rgb, uint32_t n_pixels,
+                               float inv_spp) {
+    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= n_pixels) return;
+    const float *a = accum + 3 * (size_t)pix;
+    uint8_t out[3];
+    resolve_pixel(v3(a[0], a[1], a[2]), inv_spp, out);
+    rgb[3 * (size_t)pix + 0] = out[0], rgb[3 * (size_t)pix + 1] = out[1], rgb[3 * (size_t)pix + 2] = out[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity hooks
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK, bool SMEM>
+__global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ DevScene sc, const float *__restrict__ origins,
+                                                      const float *__restrict__ dirs, long long n, float tmin, float tmax,
+                                                      int32_t *__restrict__ id_out, float *__restrict__ t_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const F4 *nodes = sc.nodes, *sph = sc.sph;
+    const I2 *meta = sc.meta;
+    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
+    Stack stack;
+    if constexpr (SMEM) {
+        SmemScene s = stage_scene(sc, smem_raw);
+        nodes = s.nodes, sph = s.sph, meta = s.meta;
+        stack.base = s.stack + threadIdx.x;
+        stack.stride = BLOCK;
+    }
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
+        const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        HitRec h;
+        trace_closest<Stack, false>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr);
+        if (h.slot == RT_REF_NONE) {
+            id_out[i] = -1, t_out[i] = 0.0f;
+        } else {
+            id_out[i] = meta[h.slot].x, t_out[i] = h.t;
+        }
+    }
+}
+
+__global__ void primary_kernel(DevCamera cam, uint64_t seed, uint32_t pixel_begin, uint32_t sample_begin,
+                               uint32_t spp, long long n, float *__restrict__ origins, float *__restrict__ dirs) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const uint32_t pp = (uint32_t)(idx / spp), k = (uint32_t)(idx - (long long)pp * spp);
+    const uint32_t pixel = pixel_begin + pp;
+    const int j = (int)(pixel / (uint32_t)cam.width), i = (int)(pixel - (uint32_t)j * cam.width);
+    PathRng rng;
+    rng.init(seed, pixel, sample_begin + k);
+    V3 o, d;
+    generate_ray(cam, rng, i, j, o, d);
+    origins[3 * idx] = o.x, origins[3 * idx + 1] = o.y, origins[3 * idx + 2] = o.z;
+    dirs[3 * idx] = d.x, dirs[3 * idx + 1] = d.y, dirs[3 * idx + 2] = d.z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: scene handle
+// ---------------------------------------------------------------------------------------------
+struct rt_scene {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::vector<rt_sphere> spheres;
+    FlatBvh bvh;
+    double center[3] = {0, 0, 0};
+    double extent90 = 0;
+    float origin_radius = 0;
+    DevScene dev{};
+    bool use_smem = false;
+    int block = 256;
+    // device buffers
+    F4 *d_nodes = nullptr, *d_sph = nullptr, *d_mats = nullptr;
+    I2 *d_meta = nullptr;
+    DevImage *d_images = nullptr;
+    std::vector<uint16_t *> d_texels;
+    // work buffers (grown on demand)
+    float4 *d_samples = nullptr;
+    size_t samples_cap = 0;
+    unsigned int *d_counter = nullptr;
+    unsigned long long *d_stats = nullptr;
+    cudaStream_t stream = nullptr;     // stream in use
+    cudaStream_t own_stream = nullptr; // created with the handle
+    std::vector<cudaEvent_t> events;   // pairs around megakernel launches
+};
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
+extern "C" int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+extern "C" int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+static int select_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(RT_ERR_NO_DEVICE, "no CUDA device visible; librt_b200 has no CPU path");
+    }
+    if (device < 0 || device >= n) return fail(RT_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(RT_ERR_NO_DEVICE, "device %d is sm_%dx; this library is built for sm_100a only", device, major);
+    CU(cudaSetDevice(device));
+    return RT_OK;
+}
+
+static int validate_desc(const rt_scene_desc *d) {
+    if (!d) return fail(RT_ERR_INVALID_ARGUMENT, "scene desc is null");
+    if (d->abi_version != RT_B200_ABI_VERSION)
+        return fail(RT_ERR_INVALID_ARGUMENT, "abi_version %u != %d", d->abi_version, RT_B200_ABI_VERSION);
+    if ((d->n_spheres && !d->spheres) || (d->n_materials && !d->materials) || (d->n_textures && !d->textures) ||
+        (d->n_images && !d->images))
+        return fail(RT_ERR_INVALID_ARGUMENT, "null array with non-zero count");
+    if (d->n_spheres >= (1ull << 28)) return fail(RT_ERR_INVALID_ARGUMENT, "too many spheres (%llu)", (unsigned long long)d->n_spheres);
+    for (uint64_t i = 0; i < d->n_spheres; i++) {
+        const rt_sphere &s = d->spheres[i];
+        if (s.material >= d->n_materials)
+            return fail(RT_ERR_INVALID_ARGUMENT, "sphere %llu: material %u out of range", (unsigned long long)i, s.material);
+        if (!std::isfinite(s.cx) || !std::isfinite(s.cy) || !std::isfinite(s.cz) || !std::isfinite(s.r))
+            return fail(RT_ERR_INVALID_ARGUMENT, "sphere %llu: non-finite geometry", (unsigned long long)i);
+    }
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const rt_material &m = d->materials[i];
+        if (m.kind > RT_MAT_DIFFUSE_LIGHT) return fail(RT_ERR_UNSUPPORTED, "material %u: unknown kind %u", i, m.kind);
+        if ((m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT) && m.texture >= d->n_textures)
+            return fail(RT_ERR_INVALID_ARGUMENT, "material %u: texture %u out of range", i, m.texture);
+    }
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const rt_texture &t = d->textures[i];
+        if (t.kind > RT_TEX_IMAGE) return fail(RT_ERR_UNSUPPORTED, "texture %u: unknown kind %u", i, t.kind);
+        if (t.kind == RT_TEX_IMAGE && t.image >= d->n_images)
+            return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: image %u out of range", i, t.image);
+    }
+    for (uint32_t i = 0; i < d->n_images; i++)
+        if (d->images[i].w > 0 && d->images[i].h > 0 && !d->images[i].rgb16)
+            return fail(RT_ERR_INVALID_ARGUMENT, "image %u: null texels", i);
+    return RT_OK;
+}
+
+static void free_scene(rt_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_nodes), cudaFree(s->d_sph), cudaFree(s->d_mats), cudaFree(s->d_meta), cudaFree(s->d_images);
+    for (auto p : s->d_texels) cudaFree(p);
+    cudaFree(s->d_samples), cudaFree(s->d_counter), cudaFree(s->d_stats);
+    for (auto e : s->events) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+static int upload_nodes(rt_scene *s) {
+    if (!s->bvh.nodes.empty())
+        CU(cudaMemcpyAsync(s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(F4), cudaMemcpyHostToDevice, s->stream));
+    return RT_OK;
+}
+
+static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s) {
+    s->device = device;
+    CU(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
+    int optin = 0;
+    CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    s->smem_optin = (size_t)optin;
+    CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+
+    s->spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
+    compute_scene_center(s->spheres.data(), s->spheres.size(), s->center, &s->extent90);
+    s->origin_radius = desc->ray_origin_radius > 0 ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
+    build_flat_bvh(s->spheres.data(), s->spheres.size(), s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh);
+
+    std::vector<F4> mats;
+    pack_materials(desc, &mats);
+
+    const size_t n_nodes = s->bvh.nodes.size() / 2, n_slots = s->bvh.sph.size();
+    CU(cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_nodes) * 32));
+    CU(cudaMalloc(&s->d_sph, std::max<size_t>(1, n_slots) * 16));
+    CU(cudaMalloc(&s->d_meta, std::max<size_t>(1, n_slots) * 8));
+    CU(cudaMalloc(&s->d_mats, std::max<size_t>(1, mats.size()) * 16));
+    {
+        int rc = upload_nodes(s);
+        if (rc != RT_OK) return rc;
+    }
+    if (n_slots) {
+        CU(cudaMemcpyAsync(s->d_sph, s->bvh.sph.data(), n_slots * 16, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_meta, s->bvh.meta.data(), n_slots * 8, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (!mats.empty()) CU(cudaMemcpyAsync(s->d_mats, mats.data(), mats.size() * 16, cudaMemcpyHostToDevice, s->stream));
+
+    // images: RGB16 -> (r, g, b, 0) uint16x4 so a texel is one 8-byte load
+    std::vector<DevImage> imgs(desc->n_images);
+    std::vector<std::vector<uint16_t>> staged(desc->n_images);
+    for (uint32_t i = 0; i < desc->n_images; i++) {
+        const rt_image &im = desc->images[i];
+        imgs[i].w = im.w, imgs[i].h = im.h, imgs[i].texels = nullptr;
+        if (im.w <= 0 || im.h <= 0) continue;
+        const size_t n = (size_t)im.w * im.h;
+        staged[i].resize(n * 4);
+        for (size_t k = 0; k < n; k++) {
+            staged[i][4 * k] = im.rgb16[3 * k], staged[i][4 * k + 1] = im.rgb16[3 * k + 1];
+            staged[i][4 * k + 2] = im.rgb16[3 * k + 2], staged[i][4 * k + 3] = 0;
+        }
+        uint16_t *dp = nullptr;
+        CU(cudaMalloc(&dp, n * 8));
+        s->d_texels.push_back(dp);
+        CU(cudaMemcpyAsync(dp, staged[i].data(), n * 8, cudaMemcpyHostToDevice, s->stream));
+        imgs[i].texels = dp;
+    }
+    CU(cudaMalloc(&s->d_images, std::max<size_t>(1, imgs.size()) * sizeof(DevImage)));
+    if (!imgs.empty())
+        CU(cudaMemcpyAsync(s->d_images, imgs.data(), imgs.size() * sizeof(DevImage), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMalloc(&s->d_counter, sizeof(unsigned int)));
+    CU(cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long)));
+    CU(cudaStreamSynchronize(s->stream));
+
+    s->dev.nodes = s->d_nodes, s->dev.sph = s->d_sph, s->dev.meta = s->d_meta, s->dev.mats = s->d_mats;
+    s->dev.images = s->d_images;
+    s->dev.root_ref = s->bvh.root_ref;
+    s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
+    s->dev.stack_depth = s->bvh.max_depth + 2;
+    s->block = env_int("RT_B200_BLOCK", 256);
+    if (s->block != 256 && s->block != 512 && s->block != 1024) s->block = 256;
+    const size_t budget = std::min<size_t>(s->smem_optin, 200 * 1024);
+    s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
+                  smem_total_bytes(s->dev, s->block) <= budget;
+    return RT_OK;
+}
+
+extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out) {
+    if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc != RT_OK) return rc;
+    rc = select_device(device);
+    if (rc != RT_OK) return rc;
+    rt_scene *s = new rt_scene();
+    rc = scene_create_impl(desc, device, s);
+    if (rc != RT_OK) {
+        free_scene(s);
+        return rc;
+    }
+    *out = s;
+    return RT_OK;
+}
+
+extern "C" void rt_scene_destroy(rt_scene *scene) { free_scene(scene); }
+
+extern "C" int rt_scene_set_stream(rt_scene *scene, void *cuda_stream) {
+    if (!scene) return fail(RT_ERR_INVALID_ARGUMENT, "scene is null");
+    CU(cudaSetDevice(scene->device));
+    CU(cudaStreamSynchronize(scene->stream));
+    scene->stream = cuda_stream ? (cudaStream_t)cuda_stream : scene->own_stream;
+    return RT_OK;
+}
+
+// Grow the BVH padding when ray origins lie outside the radius it was built for.
+static int ensure_origin_radius(rt_scene *s, double needed) {
+    if (needed <= s->origin_radius || s->spheres.empty()) return RT_OK;
+    s->origin_radius = (float)(needed * 1.25);
+    refit_flat_bvh(s->spheres.data(), s->spheres.size(), s->origin_radius, &s->bvh);
+    int rc = upload_nodes(s);
+    if (rc != RT_OK) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return RT_OK;
+}
+
+static double dist_to_center(const rt_scene *s, const float *p) {
+    double dx = p[0] - s->center[0], dy = p[1] - s->center[1], dz = p[2] - s->center[2];
+    return std::sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK, bool SMEM, bool COUNT>
+static int launch_render_t(rt_scene *s, const RenderParams &p) {
+    auto kern = render_kernel<BLOCK, SMEM, COUNT>;
+    const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+    if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
+    const int grid = s->sm_count * per_sm;
+    kern<<<grid, BLOCK, smem, s->stream>>>(p);
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+template <bool SMEM, bool COUNT>
+static int launch_render_b(rt_scene *s, const RenderParams &p) {
+    switch (s->block) {
+    case 256: return launch_render_t<256, SMEM, COUNT>(s, p);
+    case 1024: return launch_render_t<1024, SMEM, COUNT>(s, p);
+    default: return launch_render_t<512, SMEM, COUNT>(s, p);
+    }
+}
+
+static int launch_render(rt_scene *s, const RenderParams &p, bool count) {
+    if (s->use_smem) return count ? launch_render_b<true, true>(s, p) : launch_render_b<true, false>(s, p);
+    return count ? launch_render_b<false, true>(s, p) : launch_render_b<false, false>(s, p);
+}
+
+static int check_camera(const rt_camera *c) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "camera is null");
+    if (c->width < 1 || c->height < 1) return fail(RT_ERR_INVALID_ARGUMENT, "bad image size %dx%d", c->width, c->height);
+    if ((int64_t)c->width * c->height > (1ll << 31) - 1) return fail(RT_ERR_INVALID_ARGUMENT, "image too large");
+    if (c->max_depth < 0) return fail(RT_ERR_INVALID_ARGUMENT, "negative max_depth");
+    return RT_OK;
+}
+
+#define RT_PASS_PATHS (32u << 20) /* paths per megakernel launch: 512 MiB of float4 radiances */
+
+// Accumulate samples [sample_offset, +sample_count) of every pixel into d_accum (device, W*H*3).
+static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts *opts, float *d_accum,
+                        rt_stats *stats, uint32_t *launches) {
+    const uint32_t n_pix = (uint32_t)cam->width * (uint32_t)cam->height;
+    const int spp = opts->sample_count > 0 ? opts->sample_count : cam->spp;
+    if (spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "sample count %d < 1", spp);
+    if (opts->sample_offset < 0) return fail(RT_ERR_INVALID_ARGUMENT, "negative sample_offset");
+    const bool count = (opts->flags & RT_FLAG_COUNT_WORK) != 0;
+    // the camera may sit outside the radius the BVH was padded for
+    const float lens = std::sqrt(cam->defocus_u[0] * cam->defocus_u[0] + cam->defocus_u[1] * cam->defocus_u[1] +
+                                 cam->defocus_u[2] * cam->defocus_u[2]);
+    int rc = ensure_origin_radius(s, dist_to_center(s, cam->center) + 2.0 * lens);
+    if (rc != RT_OK) return rc;
+
+    const uint32_t budget = (uint32_t)std::max(1, env_int("RT_B200_PASS_PATHS", (int)RT_PASS_PATHS));
+    const uint32_t pix_tile = std::min(n_pix, budget);
+    const uint32_t spp_pass_max = std::max(1u, budget / pix_tile);
+    const size_t need = (size_t)pix_tile * std::min<uint32_t>(spp_pass_max, (uint32_t)spp);
+    if (need > s->samples_cap) {
+        cudaFree(s->d_samples);
+        s->d_samples = nullptr, s->samples_cap = 0;
+        CU(cudaMalloc(&s->d_samples, need * sizeof(float4)));
+        s->samples_cap = need;
+    }
+    CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), s->stream));
+
+    if (cam->max_depth <= 0) { // ray.go:33-35: every sample is black
+        CU(cudaMemsetAsync(d_accum, 0, (size_t)n_pix * 3 * sizeof(float), s->stream));
+        if (stats) stats->samples = (uint64_t)n_pix * (uint64_t)spp;
+        return RT_OK;
+    }
+    size_t n_ev = 0;
+    RenderParams p;
+    p.sc = s->dev;
+    p.cam = make_dev_camera(*cam);
+    p.seed = opts->seed;
+    p.samples = s->d_samples;
+    p.counter = s->d_counter;
+    p.stats = s->d_stats;
+    for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
+        const uint32_t np = std::min(pix_tile, n_pix - pb);
+        for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {
+            const uint32_t sp = std::min(spp_pass_max, (uint32_t)spp - k0);
+            p.pixel_begin = pb;
+            p.sample_begin = (uint32_t)opts->sample_offset + k0;
+            p.spp_pass = sp;
+            p.total_paths = np * sp;
+            CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), s->stream));
+            if (s->events.size() < n_ev + 2) {
+                cudaEvent_t a, b;
+                CU(cudaEventCreate(&a));
+                CU(cudaEventCreate(&b));
+                s->events.push_back(a), s->events.push_back(b);
+            }
+            CU(cudaEventRecord(s->events[n_ev], s->stream));
+            rc = launch_render(s, p, count);
+            if (rc != RT_OK) return rc;
+            CU(cudaEventRecord(s->events[n_ev + 1], s->stream));
+            n_ev += 2;
+            reduce_kernel<<<(np + 127) / 128, 128, 0, s->stream>>>(s->d_samples, d_accum, pb, np, sp, k0 == 0);
+            CU(cudaGetLastError());
+            *launches += 2;
+        }
+    }
+    if (stats) {
+        unsigned long long h[4];
+        CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        stats->samples = (uint64_t)n_pix * (uint64_t)spp;
+        stats->rays = h[0], stats->hits = h[1], stats->box_tests = h[2], stats->sphere_tests = h[3];
+        float total = 0;
+        for (size_t e = 0; e < n_ev; e += 2) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, s->events[e], s->events[e + 1]));
+            total += ms;
+        }
+        stats->ms_megakernel = total, stats->megakernel_launches = (uint32_t)(n_ev / 2);
+    }
+    return RT_OK;
+}
+
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int rt_render_accum_device(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts,
+                                      float *d_accum, rt_stats *stats) {
+    if (!scene || !opts || !d_accum) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_camera(camera);
+    if (rc != RT_OK) return rc;
+    const double t0 = now_ms();
+    CU(cudaSetDevice(scene->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, scene->stream));
+    uint32_t launches = 0;
+    rc = render_accum(scene, camera, opts, d_accum, stats, &launches);
+    if (rc == RT_OK) {
+        cudaEventRecord(e1, scene->stream);
+        cudaError_t e = cudaStreamSynchronize(scene->stream);
+        if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
+        float ms = 0;
+        if (rc == RT_OK) cudaEventElapsedTime(&ms, e0, e1);
+        if (stats) stats->ms_render = ms, stats->ms_total = (float)(now_ms() - t0), stats->kernel_launches = launches;
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    return rc;
+}
+
+extern "C" int rt_resolve_device(const float *d_accum, int32_t width, int32_t height, int32_t total_spp,
+                                 int32_t device, void *cuda_stream, uint8_t *rgb_out) {
+    if (!d_accum || !rgb_out || width < 1 || height < 1 || total_spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "bad argument");
+    int rc = select_device(device);
+    if (rc != RT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint32_t n_pix = (uint32_t)width * (uint32_t)height;
+    uint8_t *d_rgb = nullptr;
+    CU(cudaMalloc(&d_rgb, (size_t)n_pix * 3));
+    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st>>>(d_accum, d_rgb, n_pix, 1.0f / (float)total_spp);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb_out, d_rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_rgb);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "resolve failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts, uint8_t *rgb_out,
+                         float *accum_out, rt_stats *stats) {
+    if (!scene || !opts || !rgb_out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_camera(camera);
+    if (rc != RT_OK) return rc;
+    const double t0 = now_ms();
+    CU(cudaSetDevice(scene->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)camera->height;
+    const int spp = opts->sample_count > 0 ? opts->sample_count : camera->spp;
+    float *d_accum = nullptr;
+    uint8_t *d_rgb = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_accum), cudaFree(d_rgb);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define CU2(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            cleanup();                                                                             \
+            return fail(e__ == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA,     \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                          \
+        }                                                                                          \
+    } while (0)
+    CU2(cudaMalloc(&d_accum, (size_t)n_pix * 3 * sizeof(float)));
+    CU2(cudaMalloc(&d_rgb, (size_t)n_pix * 3));
+    CU2(cudaEventCreate(&e0));
+    CU2(cudaEventCreate(&e1));
+    CU2(cudaEventRecord(e0, scene->stream));
+    uint32_t launches = 0;
+    rc = render_accum(scene, camera, opts, d_accum, stats, &launches);
+    if (rc != RT_OK) {
+        cleanup();
+        return rc;
+    }
+    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, scene->stream>>>(d_accum, d_rgb, n_pix, 1.0f / (float)spp);
+    launches++;
+    CU2(cudaGetLastError());
+    CU2(cudaEventRecord(e1, scene->stream));
+    CU2(cudaMemcpyAsync(rgb_out, d_rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, scene->stream));
+    if (accum_out)
+        CU2(cudaMemcpyAsync(accum_out, d_accum, (size_t)n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, scene->stream));
+    CU2(cudaStreamSynchronize(scene->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (stats) stats->ms_render = ms, stats->ms_total = (float)(now_ms() - t0), stats->kernel_launches = launches;
+    cleanup();
+#undef CU2
+    return RT_OK;
+}
+
+template <int BLOCK>
+static int launch_trace_t(rt_scene *s, const float *d_o, const float *d_d, int64_t n, float tmin, float tmax,
+                          int32_t *d_id, float *d_t) {
+    const int grid = (int)std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)s->sm_count * 16);
+    if (s->use_smem) {
+        auto kern = trace_kernel<BLOCK, true>;
+        const size_t smem = smem_total_bytes(s->dev, BLOCK);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<std::min(grid, s->sm_count * 2), BLOCK, smem, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);
+    } else {
+        trace_kernel<BLOCK, false><<<grid, BLOCK, 0, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);
+    }
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+extern "C" int rt_trace(rt_scene *scene, const float *origins, const float *dirs, int64_t n, float tmin, float tmax,
+                        int32_t *id_out, float *t_out) {
+    if (!scene || n < 0 || (n && (!origins || !dirs || !id_out || !t_out))) return fail(RT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (n == 0) return RT_OK;
+    CU(cudaSetDevice(scene->device));
+    double far = 0;
+    for (int64_t i = 0; i < n; i++) far = std::max(far, dist_to_center(scene, origins + 3 * i));
+    if (!std::isfinite(far)) return fail(RT_ERR_INVALID_ARGUMENT, "non-finite ray origin");
+    int rc = ensure_origin_radius(scene, far);
+    if (rc != RT_OK) return rc;
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    int32_t *d_id = nullptr;
+    auto cleanup = [&]() { cudaFree(d_o), cudaFree(d_d), cudaFree(d_t), cudaFree(d_id); };
+    cudaError_t e = cudaMalloc(&d_o, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_t, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_id, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice, scene->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, scene->stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA, "rt_trace setup: %s", cudaGetErrorString(e));
+    }
+    rc = scene->block == 256 ? launch_trace_t<256>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t)
+                             : launch_trace_t<512>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t);
+    if (rc == RT_OK) {
+        e = cudaMemcpyAsync(id_out, d_id, (size_t)n * 4, cudaMemcpyDeviceToHost, scene->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(t_out, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, scene->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(scene->stream);
+        if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "rt_trace: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
+extern "C" int rt_primary_rays(const rt_camera *camera, const rt_render_opts *opts, int64_t pixel_begin, int64_t n_pixels,
+                               float *origins_out, float *dirs_out) {
+    if (!opts || !origins_out || !dirs_out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_camera(camera);
+    if (rc != RT_OK) return rc;
+    const int spp = opts->sample_count > 0 ? opts->sample_count : camera->spp;
+    if (pixel_begin < 0 || n_pixels < 0 || pixel_begin + n_pixels > (int64_t)camera->width * camera->height || spp < 1)
+        return fail(RT_ERR_INVALID_ARGUMENT, "pixel/sample range out of bounds");
+    rc = select_device(opts->device);
+    if (rc != RT_OK) return rc;
+    const int64_t n = n_pixels * spp;
+    if (n == 0) return RT_OK;
+    float *d_o = nullptr, *d_d = nullptr;
+    cudaError_t e = cudaMalloc(&d_o, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, (size_t)n * 12);
+    if (e == cudaSuccess) {
+        primary_kernel<<<(unsigned)((n + 255) / 256), 256>>>(make_dev_camera(*camera), opts->seed, (uint32_t)pixel_begin,
+                                                             (uint32_t)opts->sample_offset, (uint32_t)spp, n, d_o, d_d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(origins_out, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dirs_out, d_d, (size_t)n * 12, cudaMemcpyDeviceToHost);
+    cudaFree(d_o), cudaFree(d_d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "rt_primary_rays: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-only helpers
+// ---------------------------------------------------------------------------------------------
+// Camera.init, camera.go:128-166 (float32, unfused: this file is compiled with -ffp-contract=off).
+extern "C" int rt_camera_from_options(const rt_camera_options *o, rt_camera *c) {
+    if (!o || !c) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    if (o->image_width < 1 || !(o->aspect_ratio > 0)) return fail(RT_ERR_INVALID_ARGUMENT, "bad image width / aspect");
+    const V3 look_from = v3(o->look_from[0], o->look_from[1], o->look_from[2]);
+    const V3 look_at = v3(o->look_at[0], o->look_at[1], o->look_at[2]);
+    const V3 vup = v3(o->vup[0], o->vup[1], o->vup[2]);
+    const float image_width = (float)o->image_width;               // camera.go:107
+    const V3 center = look_from;                                   // :130
+    const V3 dist = look_from - look_at;                           // :132
+    const float h = (float)tan((double)(o->fov_radians / 2.0f));   // :134
+    const float viewport_height = 2.0f * h * o->focus_dist;        // :135
+    float image_height = (float)(floor((double)image_width) / (double)o->aspect_ratio); // :137
+    if (image_height < 1) image_height = 1;
+    const float viewport_width = viewport_height * (image_width / image_height); // :141
+    const V3 w = unit(dist);
+    auto cross = [](V3 l, V3 r) { return v3(l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x); };
+    const V3 u = unit(cross(vup, w));
+    const V3 v = cross(w, u);
+    const V3 viewport_u = u * viewport_width;
+    const V3 viewport_v = v * -viewport_height;
+    const V3 du = viewport_u * (1 / image_width);
+    const V3 dv = viewport_v * (1 / image_height);
+    V3 ul = center;
+    ul = ul - w * o->focus_dist;
+    ul = ul - viewport_u * 0.5f;
+    ul = ul - viewport_v * 0.5f;
+    const V3 pixel00 = ul + (du + dv) * 0.5f;
+    const float defocus_radius = o->focus_dist * (float)tan((double)(o->defocus_angle_radians / 2.0f));
+    const V3 disk_u = u * defocus_radius, disk_v = v * defocus_radius;
+    auto put = [](float *dst, V3 s) { dst[0] = s.x, dst[1] = s.y, dst[2] = s.z; };
+    c->width = (int32_t)image_width, c->height = (int32_t)image_height;
+    c->spp = o->spp, c->max_depth = o->max_depth;
+    put(c->center, center), put(c->pixel00, pixel00), put(c->pixel_du, du), put(c->pixel_dv, dv);
+    put(c->defocus_u, disk_u), put(c->defocus_v, disk_v);
+    c->defocus_angle = o->defocus_angle_radians;
+    c->background[0] = o->background[0], c->background[1] = o->background[1], c->background[2] = o->background[2];
+    return RT_OK;
+}
+
+extern "C" int rt_scene_bvh_info(const rt_scene *s, rt_bvh_info *out) {
+    if (!s || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    out->n_nodes = s->bvh.nodes.size() / 2, out->n_slots = s->bvh.sph.size();
+    out->max_depth = s->bvh.max_depth, out->in_shared_memory = s->use_smem ? 1 : 0;
+    out->root_ref = s->bvh.root_ref, out->reserved = 0;
+    out->box_pad_min = s->bvh.pad_min, out->box_pad_max = s->bvh.pad_max;
+    return RT_OK;
+}
+
+extern "C" int rt_scene_bvh_copy(const rt_scene *s, uint32_t *nodes_out, int32_t *slot_ids_out) {
+    if (!s) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    if (nodes_out && !s->bvh.nodes.empty()) memcpy(nodes_out, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(F4));
+    if (slot_ids_out)
+        for (size_t i = 0; i < s->bvh.meta.size(); i++) slot_ids_out[i] = s->bvh.meta[i].x;
+    return RT_OK;
+}

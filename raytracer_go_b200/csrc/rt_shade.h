@@ -1,0 +1,212 @@
+// rt_shade.h — ray generation, hit completion, materials, textures and pixel resolve, in the
+// reference's float32 operation order.  __host__ __device__ for the same reason as rt_math.h.
+//
+//   camera.go:265-299   GetRay / sampleUnitSquare        -> generate_ray
+//   hittables.go:118-128, 22-37  point, normal, front    -> complete_hit
+//   hittables.go:122-126 sphere UV (only image textures) -> sphere_uv
+//   materials.go:33-42 / 60-75 / 91-119 / 301-313        -> shade_hit
+//   materials.go:127-137 / 155-157 / 175-193             -> texture_value
+//   camera.go:261 + vec3.go:145-166 + 141-143            -> resolve_pixel
+#ifndef RT_SHADE_H
+#define RT_SHADE_H
+
+#include "rt_math.h"
+#include "rt_rng.h"
+#include "rt_trace.h"
+#include "../../include/rt_b200.h"
+
+// Device material record = 2 x F4 (texture folded into the material at upload):
+//   m0 = (c0.r, c0.g, c0.b, p0)   m1 = (c1.r, c1.g, c1.b, bits(code))
+//   code = material kind | texture kind << 4 | image index << 8
+//   Lambertian/DiffuseLight + solid  : c0 = colour
+//                          + checker : c0 = even, c1 = odd, p0 = 1/scale (materials.go:128)
+//                          + image   : c0 = out-of-bounds colour
+//   Metal      : c0 = albedo, p0 = fuzz
+//   Dielectric : p0 = ior, c1.r = 1/ior (materials.go:94)
+#define RT_CODE(mat, tex, img) ((uint32_t)(mat) | ((uint32_t)(tex) << 4) | ((uint32_t)(img) << 8))
+#define RT_CODE_MAT(c) ((c) & 15u)
+#define RT_CODE_TEX(c) (((c) >> 4) & 15u)
+#define RT_CODE_IMG(c) ((c) >> 8)
+
+struct DevImage {
+    const uint16_t *texels; // 4 x uint16 per texel (r, g, b, 0), row-major
+    int32_t w, h;
+};
+
+struct DevCamera {
+    V3 center, pixel00, du, dv, disk_u, disk_v, background;
+    int32_t width, height, max_depth;
+    int32_t defocus; // defocusAngleRadians > 0, camera.go:279
+};
+
+RT_HD DevCamera make_dev_camera(const rt_camera &c) {
+    DevCamera d;
+    d.center = v3(c.center[0], c.center[1], c.center[2]);
+    d.pixel00 = v3(c.pixel00[0], c.pixel00[1], c.pixel00[2]);
+    d.du = v3(c.pixel_du[0], c.pixel_du[1], c.pixel_du[2]);
+    d.dv = v3(c.pixel_dv[0], c.pixel_dv[1], c.pixel_dv[2]);
+    d.disk_u = v3(c.defocus_u[0], c.defocus_u[1], c.defocus_u[2]);
+    d.disk_v = v3(c.defocus_v[0], c.defocus_v[1], c.defocus_v[2]);
+    d.background = v3(c.background[0], c.background[1], c.background[2]);
+    d.width = c.width, d.height = c.height, d.max_depth = c.max_depth;
+    d.defocus = c.defocus_angle > 0 ? 1 : 0;
+    return d;
+}
+
+// camera.go:265-299.  Draw order: dx, dy, then disk pairs until x^2+y^2 < 1 (always drawn, :277).
+RT_HD void generate_ray(const DevCamera &c, PathRng &rng, int i, int j, V3 &origin, V3 &dir) {
+    V3 du_off = c.du * (float)i;
+    V3 dv_off = c.dv * (float)j;
+    V3 pc = c.pixel00;
+    pc = pc + du_off;
+    pc = pc + dv_off;
+    float dx = -0.5f + rng.f32();
+    float dy = -0.5f + rng.f32();
+    pc = pc + (c.du * dx + c.dv * dy);
+    float sx, sy;
+    for (;;) { // vec3.go:203-210
+        sx = rng.range(-1.0f, 1.0f);
+        sy = rng.range(-1.0f, 1.0f);
+        if (sx * sx + sy * sy + 0.0f * 0.0f < 1.0f) break;
+    }
+    origin = c.center;
+    if (c.defocus) origin = c.center + (c.disk_u * sx + c.disk_v * sy);
+    dir = pc - origin;
+}
+
+struct HitInfo {
+    V3 point, normal;
+    bool front;
+};
+
+// hittables.go:118-120 and NewHitInfo (hittables.go:22-37)
+RT_HD void complete_hit(const F4 &s, V3 o, V3 d, float t, HitInfo &hi) {
+    V3 point = d * t + o;                                 // ray.go:25-30
+    V3 norm = unit((point - v3(s.x, s.y, s.z)) * s.w);    // hittables.go:119-120
+    bool front = dot(d, norm) < 0;
+    if (!front) norm = norm * -1.0f;
+    hi.point = point, hi.normal = norm, hi.front = front;
+}
+
+// hittables.go:122-126.  `outward` is the normal BEFORE the front-face flip.
+RT_HD void sphere_uv(V3 outward, float &u, float &v) {
+    const float pi32 = 3.14159265358979323846f; // math.go:48
+    float theta = (float)acos(-(double)outward.y);
+    float phi = (float)(atan2(-(double)outward.z, (double)outward.x) + 3.14159265358979323846);
+    u = div32(phi + div32(5 * pi32, 12.0f), 2 * pi32);
+    v = div32(theta, pi32);
+}
+
+// materials.go:175-193
+RT_HD V3 image_texture(const DevImage &im, V3 oob, float u, float v) {
+    if (im.h <= 0) return v3(0, 1, 1);
+    u = clamp01(u);
+    v = 1 - clamp01(v);
+    float fi = u * (float)im.w;
+    float fj = v * (float)im.h;
+    int i = (int)fi, j = (int)fj;
+    if (i < 0 || i >= im.w || j < 0 || j >= im.h) return oob; // image.At outside Bounds()
+    const uint16_t *px = im.texels + ((size_t)j * (size_t)im.w + (size_t)i) * 4;
+#if defined(__CUDA_ARCH__)
+    const ushort4 t = *reinterpret_cast<const ushort4 *>(px);
+    const uint16_t r = t.x, g = t.y, b = t.z;
+#else
+    const uint16_t r = px[0], g = px[1], b = px[2];
+#endif
+    const float col_scale = (float)(1.0 / 65535.0);
+    return v3((float)r * col_scale, (float)g * col_scale, (float)b * col_scale);
+}
+
+// Texture.GetTexture for the texture folded into material record (m0, m1).
+RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, const DevImage *images, V3 point,
+                       V3 outward) {
+    const uint32_t tex = RT_CODE_TEX(code);
+    if (tex == RT_TEX_CHECKER) { // materials.go:127-137
+        const float inv = m0.w;
+        int x = (int)floorf(inv * point.x);
+        int y = (int)floorf(inv * point.y);
+        int z = (int)floorf(inv * point.z);
+        if (((x + y + z) & 1) == 0) return v3(m0.x, m0.y, m0.z);
+        return v3(m1.x, m1.y, m1.z);
+    }
+    if (tex == RT_TEX_IMAGE) {
+        float u, v;
+        sphere_uv(outward, u, v);
+        return image_texture(images[RT_CODE_IMG(code)], v3(m0.x, m0.y, m0.z), u, v);
+    }
+    return v3(m0.x, m0.y, m0.z); // materials.go:155-157
+}
+
+// materials.go:115-119
+RT_HD float reflectance(float cos_theta, float eta) {
+    float r0 = div32(1.0f - eta, 1.0f + eta);
+    r0 *= r0;
+    double x = 1 - (double)cos_theta;
+    double x2 = x * x;
+    float p5 = (float)(x2 * x2 * x); // math.Pow(x, 5)
+    return r0 + (1 - r0) * p5;
+}
+
+// One Emit + Scatter (ray.go:41-50).  Returns false when the path ends (no scatter); `emitted`
+// is always written.  On scatter, (o, d) become the scattered ray and `atten` its attenuation.
+RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F4 &sphere, float t,
+                     PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
+    HitInfo hi;
+    complete_hit(sphere, o, d, t, hi);
+    const uint32_t code = as_uint(m1.w);
+    const uint32_t kind = RT_CODE_MAT(code);
+    const V3 outward = hi.front ? hi.normal : hi.normal * -1.0f;
+    emitted = v3(0, 0, 0);
+    if (kind == RT_MAT_LAMBERTIAN) { // materials.go:33-42
+        V3 dir = hi.normal + rand_unit(rng);
+        if (near_zero(dir)) dir = hi.normal;
+        atten = texture_value(m0, m1, code, images, hi.point, outward);
+        o = hi.point, d = dir;
+        return true;
+    }
+    if (kind == RT_MAT_METAL) { // materials.go:60-75
+        V3 unit_dir = unit(d);
+        V3 reflected = reflect(unit_dir, hi.normal);
+        V3 fuzz = rand_unit(rng) * m0.w;
+        V3 scattered = reflected + fuzz;
+        if (dot(scattered, hi.normal) > 0) {
+            atten = v3(m0.x, m0.y, m0.z);
+            o = hi.point, d = scattered;
+            return true;
+        }
+        return false;
+    }
+    if (kind == RT_MAT_DIELECTRIC) { // materials.go:91-113
+        const float eta = hi.front ? m1.x : m0.w;
+        V3 unit_dir = unit(d);
+        float cos_theta = fminf(dot(unit_dir * -1.0f, hi.normal), 1.0f);
+        float sin_theta = (float)sqrt(1 - (double)(cos_theta * cos_theta));
+        bool cannot_refract = sin_theta * eta > 1.0f;
+        V3 direction;
+        if (cannot_refract || reflectance(cos_theta, eta) > rng.f32())
+            direction = reflect(unit_dir, hi.normal);
+        else
+            direction = refract(unit_dir, hi.normal, eta);
+        atten = v3(1, 1, 1);
+        o = hi.point, d = direction;
+        return true;
+    }
+    // DiffuseLight: emits its texture, never scatters (materials.go:301-313)
+    emitted = texture_value(m0, m1, code, images, hi.point, outward);
+    return false;
+}
+
+// camera.go:261 (sum * (1/spp)), vec3.go:162-166 (sqrt), 145-152 (clamp, *255.999), 141-143 (int())
+RT_HD void resolve_pixel(V3 sum, float inv_spp, uint8_t *rgb) {
+    V3 mean = sum * inv_spp;
+    float ch[3] = {mean.x, mean.y, mean.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float g = sqrt32(ch[k]);
+        g = clamp01(g);
+        g *= 255.999f;
+        rgb[k] = (g != g) ? (uint8_t)0 : (uint8_t)(int)g;
+    }
+}
+
+#endif // RT_SHADE_H

@@ -1,0 +1,179 @@
+// rt_trace.h — closest-hit query over the flattened BVH with World.Hit semantics.
+//
+// Replaces BVH.Hit (bvh.go:220-249) + Aabb.Hit (bvh.go:52-102) + Sphere.Hit's root search
+// (hittables.go:96-116).  The answer is defined by the reference's brute-force list
+// (World.Hit, hittables.go:55-72): among all spheres, the smallest accepted root, the lowest
+// object index winning exact ties.  That definition is independent of traversal order:
+//   candidate(s) = near root if tmin < near root, else far root if tmin < far root  (strict,
+//                  bvh.go:18-20), computed with the reference's float32 operation order;
+//   result       = argmin over (candidate, object index), candidates >= tmax discarded.
+// Box tests only cull; they are fused (fmaf) and conservative: boxes are padded on the host so
+// no sphere whose float32 test accepts a root can be culled (see bvh_build.cpp).
+//
+// Device layout (uploaded once, depth-first order, siblings adjacent):
+//   node i  = 2 x F4 = 32 bytes: (min.x, min.y, min.z, ref) (max.x, max.y, max.z, unused)
+//   ref     = inner: index of the first of its two children (children are nodes ref, ref+1)
+//             leaf : RT_LEAF | first_slot << 3 | (count-1)        (1..8 spheres)
+//   slot s  = F4 (cx, cy, cz, r) + I2 (object index, material index)
+#ifndef RT_TRACE_H
+#define RT_TRACE_H
+
+#include "rt_math.h"
+
+#if defined(__CUDACC__)
+#define RT_ALIGN(n) __align__(n)
+#else
+#define RT_ALIGN(n) alignas(n)
+#endif
+
+struct RT_ALIGN(16) F4 {
+    float x, y, z, w;
+};
+struct RT_ALIGN(8) I2 {
+    int32_t x, y;
+};
+
+#define RT_LEAF 0x80000000u
+#define RT_REF_NONE 0xFFFFFFFFu /* empty scene / stack bottom */
+#define RT_MAX_LEAF 8
+
+struct HitRec {
+    float t;
+    uint32_t slot; // RT_REF_NONE on miss
+};
+
+struct WorkCounters {
+    unsigned long long box_tests, sphere_tests;
+};
+
+// Per-thread traversal stack in thread-private (local) memory.
+template <int N>
+struct LocalStack {
+    uint32_t e[N];
+    int sp;
+    RT_HD void reset() { sp = 0; }
+    RT_HD void push(uint32_t r) { e[sp++] = r; }
+    RT_HD uint32_t pop() { return sp > 0 ? e[--sp] : RT_REF_NONE; }
+};
+
+// Per-thread traversal stack in shared memory: entry d of thread t lives at base[d*stride + t],
+// so a warp's accesses at one depth hit 32 distinct banks.
+struct StridedStack {
+    uint32_t *base; // already offset by the thread index
+    int stride;
+    int sp;
+    RT_HD void reset() { sp = 0; }
+    RT_HD void push(uint32_t r) {
+        base[sp * stride] = r;
+        sp++;
+    }
+    RT_HD uint32_t pop() {
+        if (sp == 0) return RT_REF_NONE;
+        sp--;
+        return base[sp * stride];
+    }
+};
+
+RT_HD float rt_fmin(float a, float b) { return fminf(a, b); } // NaN-ignoring: a NaN slab never culls
+RT_HD float rt_fmax(float a, float b) { return fmaxf(a, b); }
+
+// Reciprocal of a direction component for culling only.  A zero / denormal component would give
+// inf and then inf - inf = NaN inside the fused slab test, so it is replaced by +-1e30: a ray
+// parallel to a slab then sees (-huge, +huge) when its origin is inside the slab and an empty
+// interval when outside, which is the geometric answer.
+RT_HD float cull_rcp(float x) {
+    if (fabsf(x) < 1e-30f) return copysignf(1e30f, x);
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
+
+// Slab test of one child box against (tmin, tbest]; returns entry distance, or a value > exit when
+// missed.  inv = 1/d, noi = -(o * inv).  Conservative, not the reference's arithmetic.
+RT_HD bool box_test(const F4 &lo, const F4 &hi, V3 inv, V3 noi, float tmin, float tbest, float &tnear) {
+    float x0 = fmaf(lo.x, inv.x, noi.x), x1 = fmaf(hi.x, inv.x, noi.x);
+    float y0 = fmaf(lo.y, inv.y, noi.y), y1 = fmaf(hi.y, inv.y, noi.y);
+    float z0 = fmaf(lo.z, inv.z, noi.z), z1 = fmaf(hi.z, inv.z, noi.z);
+    float tn = rt_fmax(rt_fmax(rt_fmin(x0, x1), rt_fmin(y0, y1)), rt_fmax(rt_fmin(z0, z1), tmin));
+    float tf = rt_fmin(rt_fmin(rt_fmax(x0, x1), rt_fmax(y0, y1)), rt_fmin(rt_fmax(z0, z1), tbest));
+    tnear = tn;
+    return tn <= tf;
+}
+
+// hittables.go:96-116 for one sphere, in the reference's operation order (unfused).
+// a = |d|^2 (hittables.go:98) is hoisted: it does not depend on the sphere.
+RT_HD bool sphere_candidate(const F4 &s, V3 o, V3 d, float a, float tmin, float &t_out) {
+    V3 oc = o - v3(s.x, s.y, s.z);            // hittables.go:97
+    float half_b = dot(d, oc);                // :99
+    float c = lensq(oc) - s.w * s.w;          // :100
+    float disc = half_b * half_b - a * c;     // :102
+    if (disc < 0) return false;               // :104
+    float sqt = sqrt32(disc);                 // :108
+    float root = div32(-half_b - sqt, a);     // :110
+    if (!(tmin < root)) {
+        root = div32(-half_b + sqt, a);       // :112
+        if (!(tmin < root)) return false;
+    }
+    t_out = root;
+    return true;
+}
+
+template <class Stack, bool COUNT>
+RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sph,
+                         const I2 *__restrict__ meta, uint32_t root_ref, V3 o, V3 d, float tmin,
+                         float tmax, Stack &stack, HitRec &hit, WorkCounters *wc) {
+    const V3 inv = v3(cull_rcp(d.x), cull_rcp(d.y), cull_rcp(d.z));
+    const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+    const float a = lensq(d);
+    float tbest = tmax;
+    uint32_t best_slot = RT_REF_NONE;
+    int32_t best_id = 0x7fffffff;
+    bool have_id = false; // best_id is loaded lazily: only exact ties need it
+    stack.reset();
+    uint32_t ref = root_ref;
+    while (ref != RT_REF_NONE) {
+        if (!(ref & RT_LEAF)) {
+            const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1];
+            const F4 r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
+            float tl, tr;
+            const bool hl = box_test(l0, l1, inv, noi, tmin, tbest, tl);
+            const bool hr = box_test(r0, r1, inv, noi, tmin, tbest, tr);
+            if (COUNT) wc->box_tests += 2;
+            const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                stack.push(left_first ? rref : lref);
+                ref = left_first ? lref : rref;
+            } else if (hl) {
+                ref = lref;
+            } else if (hr) {
+                ref = rref;
+            } else {
+                ref = stack.pop();
+            }
+        } else {
+            const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
+            for (uint32_t s = first; s < first + count; s++) {
+                const F4 sp = sph[s];
+                float t;
+                if (COUNT) wc->sphere_tests += 1;
+                if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
+                if (t < tbest) {
+                    tbest = t, best_slot = s, have_id = false;
+                } else if (t == tbest && best_slot != RT_REF_NONE) {
+                    // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
+                    if (!have_id) best_id = meta[best_slot].x, have_id = true;
+                    const int32_t id = meta[s].x;
+                    if (id < best_id) best_slot = s, best_id = id;
+                }
+            }
+            ref = stack.pop();
+        }
+    }
+    hit.t = tbest;
+    hit.slot = best_slot;
+}
+
+#endif // RT_TRACE_H

@@ -1,0 +1,128 @@
+// hostsim.cpp — TEST-ONLY host compile of the per-ray device headers (rt_trace.h, rt_shade.h,
+// rt_rng.h) and of the host BVH builder, so that traversal / shading / flattening logic can be
+// checked against the oracle in this GPU-less container before GPU minutes are spent.
+// It is NOT a CPU path of the product: librt_b200.so never contains or loads this code, and only
+// `-m "not gpu"` tests build and call it.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "../../raytracer_go_b200/csrc/bvh_build.h"
+#include "../../raytracer_go_b200/csrc/rt_shade.h"
+
+namespace {
+struct HostScene {
+    FlatBvh bvh;
+    std::vector<F4> mats;
+    std::vector<DevImage> images;
+    std::vector<std::vector<uint16_t>> texels;
+};
+
+void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *s) {
+    double m[3], ext;
+    compute_scene_center(d->spheres, d->n_spheres, m, &ext);
+    float R = origin_radius > 0 ? origin_radius : (d->ray_origin_radius > 0 ? d->ray_origin_radius : (float)(2 * ext));
+    build_flat_bvh(d->spheres, d->n_spheres, R, max_leaf, &s->bvh);
+    pack_materials(d, &s->mats);
+    s->images.resize(d->n_images);
+    s->texels.resize(d->n_images);
+    for (uint32_t i = 0; i < d->n_images; i++) {
+        const rt_image &im = d->images[i];
+        size_t n = (size_t)(im.w > 0 ? im.w : 0) * (size_t)(im.h > 0 ? im.h : 0);
+        s->texels[i].resize(n * 4);
+        for (size_t k = 0; k < n; k++)
+            for (int c = 0; c < 3; c++) s->texels[i][4 * k + c] = im.rgb16[3 * k + c];
+        s->images[i].texels = s->texels[i].data(), s->images[i].w = im.w, s->images[i].h = im.h;
+    }
+}
+} // namespace
+
+extern "C" {
+
+int hs_bvh_stats(const rt_scene_desc *d, int max_leaf, float origin_radius, uint64_t *n_nodes, uint64_t *n_slots,
+                 uint32_t *max_depth, float *pad_min, float *pad_max) {
+    HostScene s;
+    load(d, max_leaf, origin_radius, &s);
+    *n_nodes = s.bvh.nodes.size() / 2, *n_slots = s.bvh.sph.size(), *max_depth = s.bvh.max_depth;
+    *pad_min = s.bvh.pad_min, *pad_max = s.bvh.pad_max;
+    return 0;
+}
+
+int hs_trace(const rt_scene_desc *d, int max_leaf, float origin_radius, const float *origins, const float *dirs,
+             int64_t n, float tmin, float tmax, int32_t *id_out, float *t_out, uint64_t *box_tests,
+             uint64_t *sphere_tests) {
+    HostScene s;
+    load(d, max_leaf, origin_radius, &s);
+    WorkCounters wc{0, 0};
+    for (int64_t i = 0; i < n; i++) {
+        LocalStack<64> stack;
+        HitRec h;
+        trace_closest<LocalStack<64>, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
+                                            v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+                                            v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmin, tmax, stack, h, &wc);
+        if (h.slot == RT_REF_NONE) id_out[i] = -1, t_out[i] = 0;
+        else id_out[i] = s.bvh.meta[h.slot].x, t_out[i] = h.t;
+    }
+    if (box_tests) *box_tests = wc.box_tests;
+    if (sphere_tests) *sphere_tests = wc.sphere_tests;
+    return 0;
+}
+
+// The megakernel's per-path loop + reduce + resolve, serially, in the same operation order.
+int hs_render(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32_t sample_offset, int32_t sample_count,
+              int32_t total_spp, int max_leaf, uint8_t *rgb_out, float *accum_out) {
+    HostScene s;
+    load(d, max_leaf, 0, &s);
+    DevCamera c = make_dev_camera(*cam);
+    const int64_t n_pix = (int64_t)cam->width * cam->height;
+    for (int64_t pix = 0; pix < n_pix; pix++) {
+        V3 sum = v3(0, 0, 0);
+        for (int k = 0; k < sample_count; k++) {
+            PathRng rng;
+            rng.init(seed, (uint32_t)pix, (uint32_t)(sample_offset + k));
+            V3 o, dir;
+            generate_ray(c, rng, (int)(pix % cam->width), (int)(pix / cam->width), o, dir);
+            V3 thr = v3(1, 1, 1), rad = v3(0, 0, 0);
+            for (int depth = 0; depth < c.max_depth;) {
+                LocalStack<64> stack;
+                HitRec h;
+                trace_closest<LocalStack<64>, false>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
+                                                     s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, nullptr);
+                if (h.slot == RT_REF_NONE) {
+                    rad = rad + thr * c.background;
+                    break;
+                }
+                const int mi = s.bvh.meta[h.slot].y;
+                V3 atten, emitted;
+                bool sc = shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[h.slot], h.t, rng, o,
+                                    dir, atten, emitted);
+                rad = rad + thr * emitted;
+                if (!sc) break;
+                thr = thr * atten;
+                depth++;
+            }
+            sum = sum + rad;
+        }
+        if (accum_out) accum_out[3 * pix] = sum.x, accum_out[3 * pix + 1] = sum.y, accum_out[3 * pix + 2] = sum.z;
+        if (rgb_out) resolve_pixel(sum, 1.0f / (float)total_spp, rgb_out + 3 * pix);
+    }
+    return 0;
+}
+
+int hs_primary_rays(const rt_camera *cam, uint64_t seed, int32_t sample_offset, int32_t sample_count, int64_t pixel_begin,
+                    int64_t n_pixels, float *origins, float *dirs) {
+    DevCamera c = make_dev_camera(*cam);
+    for (int64_t p = 0; p < n_pixels; p++)
+        for (int k = 0; k < sample_count; k++) {
+            int64_t pix = pixel_begin + p;
+            PathRng rng;
+            rng.init(seed, (uint32_t)pix, (uint32_t)(sample_offset + k));
+            V3 o, dir;
+            generate_ray(c, rng, (int)(pix % cam->width), (int)(pix / cam->width), o, dir);
+            float *po = origins + 3 * (p * sample_count + k), *pd = dirs + 3 * (p * sample_count + k);
+            po[0] = o.x, po[1] = o.y, po[2] = o.z, pd[0] = dir.x, pd[1] = dir.y, pd[2] = dir.z;
+        }
+    return 0;
+}
+}
