@@ -16,7 +16,8 @@
 // GOAMD64=v1 has no FMA), so every float32 expression below keeps the reference's operation
 // order.  The RNG is NOT the reference's (math/rand, clock-seeded, camera.go:170): it is a
 // counter-based Philox4x32-10 keyed by (seed; pixel, sample, block) — the published Random123
-// algorithm (Salmon et al., SC'11) — so that oracle and device consume identical streams.
+// algorithm (Salmon et al., SC'11) — consumed in whole blocks (layout at `struct Rng`) so that
+// oracle and device draw identical values.
 
 #include "../include/rt_b200.h"
 
@@ -121,50 +122,50 @@ inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
 
+// Stream layout: every consumer takes WHOLE blocks, block b = philox(ctr = (pixel, sample, b, 0)):
+//   GetRay: one block = (dx, dy, disk.x, disk.y), then one more block (two candidate pairs) per
+//   rejected disk pair; unit-sphere sampler: one block per trial (x, y, z, unused);
+//   Dielectric.Scatter: one block, first word.
+struct Block {
+    float u[4];
+};
 struct Rng {
     uint32_t ctr[4];
     uint32_t key[2];
-    uint32_t buf[4];
-    int pos;
     Rng(uint64_t seed, uint32_t pixel, uint32_t sample) {
         ctr[0] = pixel, ctr[1] = sample, ctr[2] = 0, ctr[3] = 0;
         key[0] = (uint32_t)seed, key[1] = (uint32_t)(seed >> 32);
-        pos = 4;
-    }
-    uint32_t u32() {
-        if (pos == 4) {
-            philox4x32_10(ctr, key, buf);
-            ctr[2]++;
-            pos = 0;
-        }
-        return buf[pos++];
     }
     // rand.Float32() is uniform on [0,1) (camera.go:290); 24 random mantissa bits.
-    float f32() { return (float)(u32() >> 8) * (1.0f / 16777216.0f); }
+    Block next() {
+        uint32_t w[4];
+        philox4x32_10(ctr, key, w);
+        ctr[2]++;
+        Block b;
+        for (int i = 0; i < 4; i++) b.u[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
+        return b;
+    }
 };
 
 // math.go:30-32
-inline float rand_range(Rng &r, float lo, float hi) { return lo + r.f32() * (hi - lo); }
-// vec3.go:178-180
-inline V3 rand_range_v3(Rng &r, float lo, float hi) {
-    float x = rand_range(r, lo, hi);
-    float y = rand_range(r, lo, hi);
-    float z = rand_range(r, lo, hi);
-    return v3(x, y, z);
-}
-// vec3.go:182-190
+inline float rand_range(float r, float lo, float hi) { return lo + r * (hi - lo); }
+// vec3.go:182-190 (vec3.go:178-180 draws x, y, z in order)
 inline V3 rand_unit(Rng &r) {
     for (;;) {
-        V3 v = rand_range_v3(r, -1, 1);
+        Block b = r.next();
+        V3 v = v3(rand_range(b.u[0], -1, 1), rand_range(b.u[1], -1, 1), rand_range(b.u[2], -1, 1));
         if (lensq(v) < 1.0f) return unit(v);
     }
 }
-// vec3.go:203-210
-inline V3 rand_in_unit_disk(Rng &r) {
+// vec3.go:203-210: `first` is the pair left over in GetRay's block
+inline V3 rand_in_unit_disk(Rng &r, float u2, float u3) {
+    V3 v = v3(rand_range(u2, -1, 1), rand_range(u3, -1, 1), 0);
+    if (lensq(v) < 1) return v;
     for (;;) {
-        float x = rand_range(r, -1, 1);
-        float y = rand_range(r, -1, 1);
-        V3 v = v3(x, y, 0);
+        Block b = r.next();
+        v = v3(rand_range(b.u[0], -1, 1), rand_range(b.u[1], -1, 1), 0);
+        if (lensq(v) < 1) return v;
+        v = v3(rand_range(b.u[2], -1, 1), rand_range(b.u[3], -1, 1), 0);
         if (lensq(v) < 1) return v;
     }
 }
@@ -518,7 +519,7 @@ inline bool material_scatter(const Scene &sc, const rt_material &m, const Ray &r
         bool cannot_refract = sin_theta * eta > 1.0f;
         V3 direction;
         // `||` short-circuits: the uniform is drawn only when refraction is possible
-        if (cannot_refract || reflectance(cos_theta, eta) > rng.f32())
+        if (cannot_refract || reflectance(cos_theta, eta) > rng.next().u[0])
             direction = reflect(unit_dir, hi.normal);
         else
             direction = refract(unit_dir, hi.normal, eta);
@@ -632,10 +633,11 @@ inline Ray get_ray(const rt_camera &c, Rng &rng, int i, int j) {
     pixel_center = add(pixel_center, du_off);
     pixel_center = add(pixel_center, dv_off);
     // sampleUnitSquare, camera.go:289-299
-    float dx = -0.5f + rng.f32();
-    float dy = -0.5f + rng.f32();
+    Block b = rng.next();
+    float dx = -0.5f + b.u[0];
+    float dy = -0.5f + b.u[1];
     pixel_center = add(pixel_center, add(scale(ld3(c.pixel_du), dx), scale(ld3(c.pixel_dv), dy)));
-    V3 disc = rand_in_unit_disk(rng); // always drawn, camera.go:277
+    V3 disc = rand_in_unit_disk(rng, b.u[2], b.u[3]); // always drawn, camera.go:277
     V3 origin = ld3(c.center);
     if (c.defocus_angle > 0)
         origin = add(ld3(c.center), add(scale(ld3(c.defocus_u), disc.x), scale(ld3(c.defocus_v), disc.y)));
@@ -676,10 +678,13 @@ int orc_camera_from_options(const rt_camera_options *o, rt_camera *out) {
 
 void orc_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { philox4x32_10(ctr, key, out); }
 
-// First n floats of the stream of (seed, pixel, sample).
+// The uniforms of the first ceil(n/4) blocks of the stream of (seed, pixel, sample).
 void orc_rng_floats(uint64_t seed, uint32_t pixel, uint32_t sample, int n, float *out) {
     Rng r(seed, pixel, sample);
-    for (int i = 0; i < n; i++) out[i] = r.f32();
+    for (int i = 0; i < n; i += 4) {
+        Block b = r.next();
+        for (int k = 0; k < 4 && i + k < n; k++) out[i + k] = b.u[k];
+    }
 }
 
 // World.Hit (mode 0) or the reference's BVH.Hit over a reference-style tree (mode 1).

@@ -125,12 +125,14 @@ struct RenderParams {
     float4 *samples;       // [total_paths] radiance of path (pixel - pixel_begin) * spp_pass + k
     unsigned int *counter; // next unclaimed path index
     unsigned long long *stats; // rays, hits, box tests, sphere tests
+    uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
 };
 
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
 
-template <int BLOCK, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(BLOCK) render_kernel(const __grid_constant__ RenderParams p) {
+// BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
+template <int BLOCK, int MINB, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats;
     const I2 *meta = p.sc.meta;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(BLOCK) render_kernel(const __grid_constant__ R
     for (;;) {
         // ---- regeneration: dead lanes take the next path indices of the warp's chunk ----
         const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-        if (dead) {
+        if (dead == 0xffffffffu || (uint32_t)__popc(dead) >= p.regen_min) {
             if (warp_next >= warp_end && !exhausted) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
@@ -321,6 +323,7 @@ struct rt_scene {
     DevScene dev{};
     bool use_smem = false;
     int block = 256;
+    int minb = 3;
     // device buffers
     F4 *d_nodes = nullptr, *d_sph = nullptr, *d_mats = nullptr;
     I2 *d_meta = nullptr;
@@ -487,6 +490,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     s->dev.stack_depth = s->bvh.max_depth + 2;
     s->block = env_int("RT_B200_BLOCK", 256);
     if (s->block != 256 && s->block != 512 && s->block != 1024) s->block = 256;
+    s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 1);
     const size_t budget = std::min<size_t>(s->smem_optin, 200 * 1024);
     s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
                   smem_total_bytes(s->dev, s->block) <= budget;
@@ -539,9 +543,9 @@ static double dist_to_center(const rt_scene *s, const float *p) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK, bool SMEM, bool COUNT>
+template <int BLOCK, int MINB, bool SMEM, bool COUNT>
 static int launch_render_t(rt_scene *s, const RenderParams &p) {
-    auto kern = render_kernel<BLOCK, SMEM, COUNT>;
+    auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT>;
     const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -553,12 +557,18 @@ static int launch_render_t(rt_scene *s, const RenderParams &p) {
     return RT_OK;
 }
 
+// (block, min blocks/SM) instances: 256x3 = 24 warps at <= 85 registers, 256x4 / 512x2 / 1024x1 =
+// 32 warps at <= 64 registers.  RT_B200_BLOCK / RT_B200_MINB pick one (tuning knob).
 template <bool SMEM, bool COUNT>
 static int launch_render_b(rt_scene *s, const RenderParams &p) {
-    switch (s->block) {
-    case 256: return launch_render_t<256, SMEM, COUNT>(s, p);
-    case 1024: return launch_render_t<1024, SMEM, COUNT>(s, p);
-    default: return launch_render_t<512, SMEM, COUNT>(s, p);
+    const int key = s->block * 10 + s->minb;
+    switch (key) {
+    case 2562: return launch_render_t<256, 2, SMEM, COUNT>(s, p);
+    case 2564: return launch_render_t<256, 4, SMEM, COUNT>(s, p);
+    case 5121: return launch_render_t<512, 1, SMEM, COUNT>(s, p);
+    case 5122: return launch_render_t<512, 2, SMEM, COUNT>(s, p);
+    case 10241: return launch_render_t<1024, 1, SMEM, COUNT>(s, p);
+    default: return launch_render_t<256, 3, SMEM, COUNT>(s, p);
     }
 }
 
@@ -616,6 +626,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.samples = s->d_samples;
     p.counter = s->d_counter;
     p.stats = s->d_stats;
+    p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", 1)));
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
         for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {

@@ -1,11 +1,19 @@
 // rt_rng.h — counter-based Philox4x32-10 stream, one per (pixel, sample) path.
 //
 // The reference draws from clock-seeded math/rand generators (camera.go:170-171, materials.go:103);
-// that stream is not reproducible and not part of any contract.  Here the stream of a path is
-//   words of Philox4x32-10( counter = (pixel, sample, block, 0), key = (seed_lo, seed_hi) ),
-// block = 0,1,2,..., consumed in order; Float32() = (word >> 8) * 2^-24  in [0,1).
-// Any (pixel, sample) can therefore be generated on any GPU in any order (sample-split /
-// tile-split renders draw exactly the samples of the single-GPU render).
+// that stream is not reproducible and not part of any contract.  Here the stream of a path is the
+// sequence of BLOCKS
+//   block b = Philox4x32-10( counter = (pixel, sample, b, 0), key = (seed_lo, seed_hi) ),  b = 0,1,2,...
+// each giving four uniforms  Float32() = (word >> 8) * 2^-24  in [0,1), and every consumer takes
+// whole blocks (a partly used block is dropped):
+//   Camera.GetRay          one block = (dx, dy, disk.x, disk.y); while the disk pair is rejected
+//                          (vec3.go:203-210) another block = two more candidate pairs, tried in order
+//   unit-sphere rejection  one block per trial = (x, y, z, unused)      (vec3.go:182-190)
+//   Dielectric.Scatter     one block, first word = the uniform of materials.go:103
+// Whole-block consumption keeps the ten Philox rounds at warp-convergent program points (every lane
+// still in a rejection loop generates together) instead of inside a per-lane "buffer empty" branch.
+// Any (pixel, sample) can be generated on any GPU in any order, so sample-split / tile-split renders
+// draw exactly the samples of the single-GPU render.
 #ifndef RT_RNG_H
 #define RT_RNG_H
 
@@ -19,57 +27,52 @@ RT_HD uint32_t rt_mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
+struct RngBlock {
+    float u0, u1, u2, u3;
+};
+
 struct PathRng {
     uint32_t pixel, sample, block;
     uint32_t k0, k1;
-    uint32_t b0, b1, b2, b3; // unread words of the current block, b0 next
-    uint32_t avail;
 
     RT_HD void init(uint64_t seed, uint32_t pixel_, uint32_t sample_) {
         pixel = pixel_, sample = sample_, block = 0;
         k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        avail = 0;
-        b0 = b1 = b2 = b3 = 0;
     }
-    RT_HD void refill() {
+    RT_HD static float to_f32(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+    // next block of the stream as four uniforms on [0,1) (rand.Float32(), camera.go:290-291)
+    RT_HD RngBlock next() {
         uint32_t c0 = pixel, c1 = sample, c2 = block, c3 = 0;
         uint32_t q0 = k0, q1 = k1;
 #pragma unroll
         for (int r = 0; r < 10; r++) {
-            uint32_t hi0 = rt_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            uint32_t hi1 = rt_mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            uint32_t n0 = hi1 ^ c1 ^ q0;
-            uint32_t n2 = hi0 ^ c3 ^ q1;
+            const uint32_t hi0 = rt_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = rt_mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ q0;
+            const uint32_t n2 = hi0 ^ c3 ^ q1;
             c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
             q0 += 0x9E3779B9u;
             q1 += 0xBB67AE85u;
         }
-        b0 = c0, b1 = c1, b2 = c2, b3 = c3;
         block++;
-        avail = 4;
+        RngBlock b;
+        b.u0 = to_f32(c0), b.u1 = to_f32(c1), b.u2 = to_f32(c2), b.u3 = to_f32(c3);
+        return b;
     }
-    RT_HD uint32_t u32() {
-        if (avail == 0) refill();
-        uint32_t r = b0;
-        b0 = b1, b1 = b2, b2 = b3;
-        avail--;
-        return r;
-    }
-    // uniform on [0,1) like rand.Float32() (camera.go:290-291)
-    RT_HD float f32() { return (float)(u32() >> 8) * (1.0f / 16777216.0f); }
-    // math.go:30-32
-    RT_HD float range(float lo, float hi) { return lo + f32() * (hi - lo); }
 };
 
-// vec3.go:182-190 (NewVec3UnitRandOnUnitSphere32): cube rejection, then Unit()
+// math.go:30-32: min + r*(max-min)
+RT_HD float rand_range(float r, float lo, float hi) { return lo + r * (hi - lo); }
+
+// vec3.go:182-190 (NewVec3UnitRandOnUnitSphere32): cube rejection, then Unit(); one block per trial
 RT_HD V3 rand_unit(PathRng &rng) {
+    V3 v;
     for (;;) {
-        float x = rng.range(-1.0f, 1.0f);
-        float y = rng.range(-1.0f, 1.0f);
-        float z = rng.range(-1.0f, 1.0f);
-        V3 v = v3(x, y, z);
-        if (lensq(v) < 1.0f) return unit(v);
+        const RngBlock b = rng.next();
+        v = v3(rand_range(b.u0, -1.0f, 1.0f), rand_range(b.u1, -1.0f, 1.0f), rand_range(b.u2, -1.0f, 1.0f));
+        if (lensq(v) < 1.0f) break;
     }
+    return unit(v); // after the loop: the sqrt and divide run once, with the lanes reconverged
 }
 
 #endif // RT_RNG_H

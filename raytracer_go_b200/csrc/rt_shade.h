@@ -53,21 +53,25 @@ RT_HD DevCamera make_dev_camera(const rt_camera &c) {
     return d;
 }
 
-// camera.go:265-299.  Draw order: dx, dy, then disk pairs until x^2+y^2 < 1 (always drawn, :277).
+// camera.go:265-299.  Draw order (rt_rng.h): one block = (dx, dy, disk.x, disk.y); while the disk
+// pair fails x^2+y^2 < 1 (vec3.go:203-210; the disk sample is always drawn, camera.go:277) another
+// block supplies two more candidate pairs.
 RT_HD void generate_ray(const DevCamera &c, PathRng &rng, int i, int j, V3 &origin, V3 &dir) {
     V3 du_off = c.du * (float)i;
     V3 dv_off = c.dv * (float)j;
     V3 pc = c.pixel00;
     pc = pc + du_off;
     pc = pc + dv_off;
-    float dx = -0.5f + rng.f32();
-    float dy = -0.5f + rng.f32();
+    RngBlock b = rng.next();
+    float dx = -0.5f + b.u0;
+    float dy = -0.5f + b.u1;
     pc = pc + (c.du * dx + c.dv * dy);
-    float sx, sy;
-    for (;;) { // vec3.go:203-210
-        sx = rng.range(-1.0f, 1.0f);
-        sy = rng.range(-1.0f, 1.0f);
+    float sx = rand_range(b.u2, -1.0f, 1.0f), sy = rand_range(b.u3, -1.0f, 1.0f);
+    while (!(sx * sx + sy * sy + 0.0f * 0.0f < 1.0f)) {
+        b = rng.next();
+        sx = rand_range(b.u0, -1.0f, 1.0f), sy = rand_range(b.u1, -1.0f, 1.0f);
         if (sx * sx + sy * sy + 0.0f * 0.0f < 1.0f) break;
+        sx = rand_range(b.u2, -1.0f, 1.0f), sy = rand_range(b.u3, -1.0f, 1.0f);
     }
     origin = c.center;
     if (c.defocus) origin = c.center + (c.disk_u * sx + c.disk_v * sy);
@@ -149,25 +153,29 @@ RT_HD float reflectance(float cos_theta, float eta) {
 
 // One Emit + Scatter (ray.go:41-50).  Returns false when the path ends (no scatter); `emitted`
 // is always written.  On scatter, (o, d) become the scattered ray and `atten` its attenuation.
+// The work shared by several materials (the unit-sphere sample of Lambertian and Metal, Unit(dir)
+// of Metal and Dielectric) is hoisted so that lanes with different materials run it together.
 RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F4 &sphere, float t,
                      PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
     HitInfo hi;
     complete_hit(sphere, o, d, t, hi);
     const uint32_t code = as_uint(m1.w);
     const uint32_t kind = RT_CODE_MAT(code);
-    const V3 outward = hi.front ? hi.normal : hi.normal * -1.0f;
     emitted = v3(0, 0, 0);
+    V3 ru = v3(0, 0, 0), unit_dir = v3(0, 0, 0);
+    if (kind == RT_MAT_LAMBERTIAN || kind == RT_MAT_METAL) ru = rand_unit(rng); // materials.go:34, 64
+    if (kind == RT_MAT_METAL || kind == RT_MAT_DIELECTRIC) unit_dir = unit(d);  // materials.go:61, 97
     if (kind == RT_MAT_LAMBERTIAN) { // materials.go:33-42
-        V3 dir = hi.normal + rand_unit(rng);
+        V3 dir = hi.normal + ru;
         if (near_zero(dir)) dir = hi.normal;
+        const V3 outward = hi.front ? hi.normal : hi.normal * -1.0f;
         atten = texture_value(m0, m1, code, images, hi.point, outward);
         o = hi.point, d = dir;
         return true;
     }
     if (kind == RT_MAT_METAL) { // materials.go:60-75
-        V3 unit_dir = unit(d);
         V3 reflected = reflect(unit_dir, hi.normal);
-        V3 fuzz = rand_unit(rng) * m0.w;
+        V3 fuzz = ru * m0.w;
         V3 scattered = reflected + fuzz;
         if (dot(scattered, hi.normal) > 0) {
             atten = v3(m0.x, m0.y, m0.z);
@@ -178,12 +186,12 @@ RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F
     }
     if (kind == RT_MAT_DIELECTRIC) { // materials.go:91-113
         const float eta = hi.front ? m1.x : m0.w;
-        V3 unit_dir = unit(d);
         float cos_theta = fminf(dot(unit_dir * -1.0f, hi.normal), 1.0f);
         float sin_theta = (float)sqrt(1 - (double)(cos_theta * cos_theta));
         bool cannot_refract = sin_theta * eta > 1.0f;
         V3 direction;
-        if (cannot_refract || reflectance(cos_theta, eta) > rng.f32())
+        // `||` short-circuits (materials.go:103): the uniform is drawn only if refraction is possible
+        if (cannot_refract || reflectance(cos_theta, eta) > rng.next().u0)
             direction = reflect(unit_dir, hi.normal);
         else
             direction = refract(unit_dir, hi.normal, eta);
@@ -192,6 +200,7 @@ RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F
         return true;
     }
     // DiffuseLight: emits its texture, never scatters (materials.go:301-313)
+    const V3 outward = hi.front ? hi.normal : hi.normal * -1.0f;
     emitted = texture_value(m0, m1, code, images, hi.point, outward);
     return false;
 }

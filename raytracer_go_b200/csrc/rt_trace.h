@@ -133,8 +133,10 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
     bool have_id = false; // best_id is loaded lazily: only exact ties need it
     stack.reset();
     uint32_t ref = root_ref;
-    while (ref != RT_REF_NONE) {
-        if (!(ref & RT_LEAF)) {
+    for (;;) {
+        // "while-while": every lane first descends through inner nodes until it holds a leaf (or
+        // nothing), then the lanes test their leaves together.  RT_REF_NONE has the leaf bit set.
+        while (!(ref & RT_LEAF)) {
             const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1];
             const F4 r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
             float tl, tr;
@@ -153,24 +155,24 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
             } else {
                 ref = stack.pop();
             }
-        } else {
-            const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
-            for (uint32_t s = first; s < first + count; s++) {
-                const F4 sp = sph[s];
-                float t;
-                if (COUNT) wc->sphere_tests += 1;
-                if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
-                if (t < tbest) {
-                    tbest = t, best_slot = s, have_id = false;
-                } else if (t == tbest && best_slot != RT_REF_NONE) {
-                    // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
-                    if (!have_id) best_id = meta[best_slot].x, have_id = true;
-                    const int32_t id = meta[s].x;
-                    if (id < best_id) best_slot = s, best_id = id;
-                }
-            }
-            ref = stack.pop();
         }
+        if (ref == RT_REF_NONE) break;
+        const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
+        for (uint32_t s = first; s < first + count; s++) {
+            const F4 sp = sph[s];
+            float t;
+            if (COUNT) wc->sphere_tests += 1;
+            if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
+            if (t < tbest) {
+                tbest = t, best_slot = s, have_id = false;
+            } else if (t == tbest && best_slot != RT_REF_NONE) {
+                // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
+                if (!have_id) best_id = meta[best_slot].x, have_id = true;
+                const int32_t id = meta[s].x;
+                if (id < best_id) best_slot = s, best_id = id;
+            }
+        }
+        ref = stack.pop();
     }
     hit.t = tbest;
     hit.slot = best_slot;

@@ -1,0 +1,90 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol include/rt_b200.h
+declares, agrees with the ctypes struct layouts, fails loudly without a device, and its host-only
+helper (Camera.init) equals the oracle's."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+from raytracer_go_b200 import abi, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rt_b200.h")
+
+
+def test_exports_every_declared_symbol(rtlib):
+    text = open(HEADER).read()
+    declared = set(re.findall(r"^(?:int|void|const char \*)\s*(rt_[a-z0-9_]+)\(", text, re.M))
+    assert declared == set(abi.PROTOTYPES), declared ^ set(abi.PROTOTYPES)
+    for name in declared:
+        assert hasattr(rtlib, name), f"librt_b200.so does not export {name}"
+    assert rtlib.rt_abi_version() == abi.RT_B200_ABI_VERSION
+
+
+def test_struct_layouts_match_the_header():
+    """Compile a probe against the real header and compare sizeof/offsetof with ctypes."""
+    structs = {n: getattr(abi, n) for n in ("rt_sphere", "rt_material", "rt_texture", "rt_image", "rt_scene_desc",
+                                           "rt_camera", "rt_camera_options", "rt_render_opts", "rt_stats",
+                                           "rt_bvh_info")}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for n, s in structs.items():
+        lines.append(f'printf("{n} %zu\\n", sizeof({n}));')
+        for f, _ in s._fields_:
+            lines.append(f'printf("{n}.{f} %zu\\n", offsetof({n}, {f}));')
+    lines.append("return 0;}")
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "p.c"), os.path.join(d, "p")
+        open(src, "w").write("\n".join(lines))
+        subprocess.check_call(["gcc", "-o", exe, src])
+        out = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for n, s in structs.items():
+        assert int(out[n]) == C.sizeof(s), n
+        for f, _ in s._fields_:
+            assert int(out[f"{n}.{f}"]) == getattr(s, f).offset, f"{n}.{f}"
+
+
+def test_no_device_is_a_loud_error(rtlib):
+    """Without a B200 every compute entry point returns RT_ERR_NO_DEVICE — there is no CPU path."""
+    if rtlib.rt_device_count() > 0:
+        return
+    desc, keep = scenes.random_scene().to_desc()
+    h = C.c_void_p()
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_NO_DEVICE
+    assert not h.value and b"no CPU path" in rtlib.rt_last_error()
+    cam = abi.rt_camera()
+    assert rtlib.rt_camera_from_options(C.byref(scenes.camera_options(64, 1)), C.byref(cam)) == 0
+    opts = abi.rt_render_opts(1, 0, 0, 1, 0)
+    buf = np.zeros((cam.width * cam.height, 3), np.float32)
+    rc = rtlib.rt_primary_rays(C.byref(cam), C.byref(opts), 0, 4, buf.ctypes.data_as(C.c_void_p),
+                               buf.ctypes.data_as(C.c_void_p))
+    assert rc == abi.RT_ERR_NO_DEVICE
+
+
+def test_invalid_arguments(rtlib):
+    h = C.c_void_p()
+    assert rtlib.rt_scene_create(None, 0, C.byref(h)) == abi.RT_ERR_INVALID_ARGUMENT
+    bad = scenes.random_scene()
+    desc, keep = bad.to_desc()
+    desc.abi_version = 99
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_INVALID_ARGUMENT
+    assert b"abi_version" in rtlib.rt_last_error()
+    bad.materials["kind"][5] = 17
+    desc, keep = bad.to_desc()
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_UNSUPPORTED
+    assert rtlib.rt_camera_from_options(None, None) == abi.RT_ERR_INVALID_ARGUMENT
+    rtlib.rt_scene_destroy(None)  # must be a no-op
+
+
+def test_camera_from_options_equals_oracle(rtlib, orc):
+    """rt_camera_from_options (host, camera.go:128-166) is bit-identical to the oracle's."""
+    cases = [scenes.camera_options(w, 7) for w in (400, 1200, 1920, 3840, 37)]
+    cases.append(scenes.camera_options(600, 3, look_from=(278, 278, -800), look_at=(278, 278, 0), vfov_deg=40,
+                                       defocus_deg=0, aspect=1.0, background=(0, 0, 0)))
+    cases.append(scenes.camera_options(400, 3, look_from=(0, 0, 12), defocus_deg=0))
+    for o in cases:
+        a, b = abi.rt_camera(), orc.camera_from_options(o)
+        assert rtlib.rt_camera_from_options(C.byref(o), C.byref(a)) == 0
+        assert bytes(a) == bytes(b)
