@@ -174,6 +174,9 @@ int rt_device_count(void);
  * depth-first order, and uploads nodes / spheres / materials / texels once. */
 int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out);
 void rt_scene_destroy(rt_scene *scene);
+/* Frees the per-device work buffers the library caches across handles (per-pass radiance buffer,
+ * accumulator, RGB8 staging); device < 0 = every device.  They are re-allocated on demand. */
+void rt_workspace_release(int device);
 /* Run this handle's kernels and copies on the caller's CUDA stream (a cudaStream_t; NULL restores
  * the handle's own stream).  Lets a host framework order the render with its own work (e.g. an
  * NCCL reduce of the accumulators) and time it with events on that stream. */

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "rt_scene_create": (C.c_int, [C.POINTER(rt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]),
     "rt_scene_destroy": (None, [C.c_void_p]),
     "rt_scene_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_workspace_release": (None, [C.c_int]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_opts),
                             C.c_void_p, C.c_void_p, C.POINTER(rt_stats)]),
     "rt_render_accum_device": (C.c_int, [C.c_void_p, C.POINTER(rt_camera),

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -309,6 +310,63 @@ __global__ void primary_kernel(DevCamera cam, uint64_t seed, uint32_t pixel_begi
 }
 
 // ---------------------------------------------------------------------------------------------
+// host side: per-device workspace, shared by all scene handles of the process
+// ---------------------------------------------------------------------------------------------
+// The per-pass radiance buffer (up to 512 MiB), the accumulator, the RGB8 image and its pinned
+// staging copy are cached per device for the life of the process (rt_workspace_release frees
+// them): a Camera.Render-style call creates and destroys a scene handle every time, and paying a
+// half-gigabyte cudaMalloc/cudaFree per call costs more than the render itself.  The mutex is held
+// for the duration of a render or resolve, which serialises calls on one device (they would
+// serialise on the GPU anyway) and keeps distinct handles independent as far as results go.
+#define RT_MAX_DEVICES 64
+struct Workspace {
+    std::mutex mu;
+    float4 *samples = nullptr;
+    size_t samples_cap = 0; // elements
+    float *accum = nullptr;
+    size_t accum_cap = 0; // floats
+    uint8_t *rgb = nullptr, *h_rgb = nullptr;
+    size_t rgb_cap = 0, h_rgb_cap = 0; // bytes
+    float *h_accum = nullptr;
+    size_t h_accum_cap = 0; // floats (pinned)
+};
+static Workspace g_ws[RT_MAX_DEVICES];
+
+template <class T>
+static int ws_reserve(T *&ptr, size_t &cap, size_t need, bool pinned_host = false) {
+    if (need <= cap) return RT_OK;
+    if (ptr) {
+        if (pinned_host) cudaFreeHost(ptr);
+        else cudaFree(ptr);
+    }
+    ptr = nullptr, cap = 0;
+    if (pinned_host) CU(cudaMallocHost((void **)&ptr, need * sizeof(T)));
+    else CU(cudaMalloc((void **)&ptr, need * sizeof(T)));
+    cap = need;
+    return RT_OK;
+}
+
+extern "C" void rt_workspace_release(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (int d = 0; d < n && d < RT_MAX_DEVICES; d++) {
+        if (device >= 0 && d != device) continue;
+        Workspace &w = g_ws[d];
+        std::lock_guard<std::mutex> lock(w.mu);
+        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum) continue;
+        cudaSetDevice(d);
+        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb);
+        if (w.h_rgb) cudaFreeHost(w.h_rgb);
+        if (w.h_accum) cudaFreeHost(w.h_accum);
+        w.samples = nullptr, w.accum = nullptr, w.rgb = nullptr, w.h_rgb = nullptr, w.h_accum = nullptr;
+        w.samples_cap = w.accum_cap = w.rgb_cap = w.h_rgb_cap = w.h_accum_cap = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: scene handle
 // ---------------------------------------------------------------------------------------------
 struct rt_scene {
@@ -329,9 +387,8 @@ struct rt_scene {
     I2 *d_meta = nullptr;
     DevImage *d_images = nullptr;
     std::vector<uint16_t *> d_texels;
-    // work buffers (grown on demand)
-    float4 *d_samples = nullptr;
-    size_t samples_cap = 0;
+    int grid_cache[2] = {0, 0};  // persistent grid size of the plain / counting megakernel
+    size_t smem_cache[2] = {0, 0};
     unsigned int *d_counter = nullptr;
     unsigned long long *d_stats = nullptr;
     cudaStream_t stream = nullptr;     // stream in use
@@ -413,7 +470,7 @@ static void free_scene(rt_scene *s) {
     cudaSetDevice(s->device);
     cudaFree(s->d_nodes), cudaFree(s->d_sph), cudaFree(s->d_mats), cudaFree(s->d_meta), cudaFree(s->d_images);
     for (auto p : s->d_texels) cudaFree(p);
-    cudaFree(s->d_samples), cudaFree(s->d_counter), cudaFree(s->d_stats);
+    cudaFree(s->d_counter), cudaFree(s->d_stats);
     for (auto e : s->events) cudaEventDestroy(e);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -546,13 +603,16 @@ static double dist_to_center(const rt_scene *s, const float *p) {
 template <int BLOCK, int MINB, bool SMEM, bool COUNT>
 static int launch_render_t(rt_scene *s, const RenderParams &p) {
     auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT>;
-    const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
-    if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
-    const int grid = s->sm_count * per_sm;
-    kern<<<grid, BLOCK, smem, s->stream>>>(p);
+    if (s->grid_cache[COUNT] == 0) { // once per handle: opt in to the dynamic shared memory, size the grid
+        const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+        if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
+        s->grid_cache[COUNT] = s->sm_count * per_sm; // persistent: one wave of resident CTAs
+        s->smem_cache[COUNT] = smem;
+    }
+    kern<<<s->grid_cache[COUNT], BLOCK, s->smem_cache[COUNT], s->stream>>>(p);
     CU(cudaGetLastError());
     return RT_OK;
 }
@@ -585,6 +645,15 @@ static int check_camera(const rt_camera *c) {
     return RT_OK;
 }
 
+static int scene_events(rt_scene *s, size_t n) {
+    while (s->events.size() < n) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        s->events.push_back(e);
+    }
+    return RT_OK;
+}
+
 #define RT_PASS_PATHS (32u << 20) /* paths per megakernel launch: 512 MiB of float4 radiances */
 
 // Accumulate samples [sample_offset, +sample_count) of every pixel into d_accum (device, W*H*3).
@@ -605,12 +674,9 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     const uint32_t pix_tile = std::min(n_pix, budget);
     const uint32_t spp_pass_max = std::max(1u, budget / pix_tile);
     const size_t need = (size_t)pix_tile * std::min<uint32_t>(spp_pass_max, (uint32_t)spp);
-    if (need > s->samples_cap) {
-        cudaFree(s->d_samples);
-        s->d_samples = nullptr, s->samples_cap = 0;
-        CU(cudaMalloc(&s->d_samples, need * sizeof(float4)));
-        s->samples_cap = need;
-    }
+    Workspace &ws = g_ws[s->device];
+    rc = ws_reserve(ws.samples, ws.samples_cap, need);
+    if (rc != RT_OK) return rc;
     CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), s->stream));
 
     if (cam->max_depth <= 0) { // ray.go:33-35: every sample is black
@@ -618,15 +684,15 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
         if (stats) stats->samples = (uint64_t)n_pix * (uint64_t)spp;
         return RT_OK;
     }
-    size_t n_ev = 0;
+    size_t n_ev = 2; // events 0 and 1 bracket the whole call
     RenderParams p;
     p.sc = s->dev;
     p.cam = make_dev_camera(*cam);
     p.seed = opts->seed;
-    p.samples = s->d_samples;
+    p.samples = ws.samples;
     p.counter = s->d_counter;
     p.stats = s->d_stats;
-    p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", 1)));
+    p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", 8)));
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
         for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {
@@ -636,18 +702,14 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
             p.spp_pass = sp;
             p.total_paths = np * sp;
             CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), s->stream));
-            if (s->events.size() < n_ev + 2) {
-                cudaEvent_t a, b;
-                CU(cudaEventCreate(&a));
-                CU(cudaEventCreate(&b));
-                s->events.push_back(a), s->events.push_back(b);
-            }
+            rc = scene_events(s, n_ev + 2);
+            if (rc != RT_OK) return rc;
             CU(cudaEventRecord(s->events[n_ev], s->stream));
             rc = launch_render(s, p, count);
             if (rc != RT_OK) return rc;
             CU(cudaEventRecord(s->events[n_ev + 1], s->stream));
             n_ev += 2;
-            reduce_kernel<<<(np + 127) / 128, 128, 0, s->stream>>>(s->d_samples, d_accum, pb, np, sp, k0 == 0);
+            reduce_kernel<<<(np + 127) / 128, 128, 0, s->stream>>>(ws.samples, d_accum, pb, np, sp, k0 == 0);
             CU(cudaGetLastError());
             *launches += 2;
         }
@@ -659,12 +721,12 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
         stats->samples = (uint64_t)n_pix * (uint64_t)spp;
         stats->rays = h[0], stats->hits = h[1], stats->box_tests = h[2], stats->sphere_tests = h[3];
         float total = 0;
-        for (size_t e = 0; e < n_ev; e += 2) {
+        for (size_t e = 2; e < n_ev; e += 2) {
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, s->events[e], s->events[e + 1]));
             total += ms;
         }
-        stats->ms_megakernel = total, stats->megakernel_launches = (uint32_t)(n_ev / 2);
+        stats->ms_megakernel = total, stats->megakernel_launches = (uint32_t)((n_ev - 2) / 2);
     }
     return RT_OK;
 }
@@ -680,23 +742,20 @@ extern "C" int rt_render_accum_device(rt_scene *scene, const rt_camera *camera, 
     if (rc != RT_OK) return rc;
     const double t0 = now_ms();
     CU(cudaSetDevice(scene->device));
+    std::lock_guard<std::mutex> lock(g_ws[scene->device].mu);
     if (stats) memset(stats, 0, sizeof *stats);
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, scene->stream));
+    rc = scene_events(scene, 2);
+    if (rc != RT_OK) return rc;
+    CU(cudaEventRecord(scene->events[0], scene->stream));
     uint32_t launches = 0;
     rc = render_accum(scene, camera, opts, d_accum, stats, &launches);
-    if (rc == RT_OK) {
-        cudaEventRecord(e1, scene->stream);
-        cudaError_t e = cudaStreamSynchronize(scene->stream);
-        if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "render failed: %s", cudaGetErrorString(e));
-        float ms = 0;
-        if (rc == RT_OK) cudaEventElapsedTime(&ms, e0, e1);
-        if (stats) stats->ms_render = ms, stats->ms_total = (float)(now_ms() - t0), stats->kernel_launches = launches;
-    }
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
-    return rc;
+    if (rc != RT_OK) return rc;
+    CU(cudaEventRecord(scene->events[1], scene->stream));
+    CU(cudaStreamSynchronize(scene->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, scene->events[0], scene->events[1]));
+    if (stats) stats->ms_render = ms, stats->ms_total = (float)(now_ms() - t0), stats->kernel_launches = launches;
+    return RT_OK;
 }
 
 extern "C" int rt_resolve_device(const float *d_accum, int32_t width, int32_t height, int32_t total_spp,
@@ -704,16 +763,19 @@ extern "C" int rt_resolve_device(const float *d_accum, int32_t width, int32_t he
     if (!d_accum || !rgb_out || width < 1 || height < 1 || total_spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "bad argument");
     int rc = select_device(device);
     if (rc != RT_OK) return rc;
+    if (device >= RT_MAX_DEVICES) return fail(RT_ERR_INVALID_ARGUMENT, "device ordinal too large");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const uint32_t n_pix = (uint32_t)width * (uint32_t)height;
-    uint8_t *d_rgb = nullptr;
-    CU(cudaMalloc(&d_rgb, (size_t)n_pix * 3));
-    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st>>>(d_accum, d_rgb, n_pix, 1.0f / (float)total_spp);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb_out, d_rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_rgb);
-    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "resolve failed: %s", cudaGetErrorString(e));
+    Workspace &ws = g_ws[device];
+    std::lock_guard<std::mutex> lock(ws.mu);
+    rc = ws_reserve(ws.rgb, ws.rgb_cap, (size_t)n_pix * 3);
+    if (rc == RT_OK) rc = ws_reserve(ws.h_rgb, ws.h_rgb_cap, (size_t)n_pix * 3, true);
+    if (rc != RT_OK) return rc;
+    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st>>>(d_accum, ws.rgb, n_pix, 1.0f / (float)total_spp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ws.h_rgb, ws.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(rgb_out, ws.h_rgb, (size_t)n_pix * 3);
     return RT_OK;
 }
 
@@ -724,50 +786,34 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
     if (rc != RT_OK) return rc;
     const double t0 = now_ms();
     CU(cudaSetDevice(scene->device));
+    Workspace &ws = g_ws[scene->device];
+    std::lock_guard<std::mutex> lock(ws.mu);
     if (stats) memset(stats, 0, sizeof *stats);
     const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)camera->height;
     const int spp = opts->sample_count > 0 ? opts->sample_count : camera->spp;
-    float *d_accum = nullptr;
-    uint8_t *d_rgb = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_accum), cudaFree(d_rgb);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-    };
-#define CU2(call)                                                                                  \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess) {                                                                  \
-            cleanup();                                                                             \
-            return fail(e__ == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA,     \
-                        "%s failed: %s", #call, cudaGetErrorString(e__));                          \
-        }                                                                                          \
-    } while (0)
-    CU2(cudaMalloc(&d_accum, (size_t)n_pix * 3 * sizeof(float)));
-    CU2(cudaMalloc(&d_rgb, (size_t)n_pix * 3));
-    CU2(cudaEventCreate(&e0));
-    CU2(cudaEventCreate(&e1));
-    CU2(cudaEventRecord(e0, scene->stream));
+    rc = ws_reserve(ws.accum, ws.accum_cap, (size_t)n_pix * 3);
+    if (rc == RT_OK) rc = ws_reserve(ws.rgb, ws.rgb_cap, (size_t)n_pix * 3);
+    if (rc == RT_OK) rc = ws_reserve(ws.h_rgb, ws.h_rgb_cap, (size_t)n_pix * 3, true);
+    if (rc == RT_OK && accum_out) rc = ws_reserve(ws.h_accum, ws.h_accum_cap, (size_t)n_pix * 3, true);
+    if (rc == RT_OK) rc = scene_events(scene, 2);
+    if (rc != RT_OK) return rc;
+    CU(cudaEventRecord(scene->events[0], scene->stream));
     uint32_t launches = 0;
-    rc = render_accum(scene, camera, opts, d_accum, stats, &launches);
-    if (rc != RT_OK) {
-        cleanup();
-        return rc;
-    }
-    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, scene->stream>>>(d_accum, d_rgb, n_pix, 1.0f / (float)spp);
+    rc = render_accum(scene, camera, opts, ws.accum, stats, &launches);
+    if (rc != RT_OK) return rc;
+    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, scene->stream>>>(ws.accum, ws.rgb, n_pix, 1.0f / (float)spp);
     launches++;
-    CU2(cudaGetLastError());
-    CU2(cudaEventRecord(e1, scene->stream));
-    CU2(cudaMemcpyAsync(rgb_out, d_rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, scene->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(scene->events[1], scene->stream));
+    CU(cudaMemcpyAsync(ws.h_rgb, ws.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, scene->stream));
     if (accum_out)
-        CU2(cudaMemcpyAsync(accum_out, d_accum, (size_t)n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, scene->stream));
-    CU2(cudaStreamSynchronize(scene->stream));
+        CU(cudaMemcpyAsync(ws.h_accum, ws.accum, (size_t)n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, scene->stream));
+    CU(cudaStreamSynchronize(scene->stream));
+    memcpy(rgb_out, ws.h_rgb, (size_t)n_pix * 3);
+    if (accum_out) memcpy(accum_out, ws.h_accum, (size_t)n_pix * 3 * sizeof(float));
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
+    CU(cudaEventElapsedTime(&ms, scene->events[0], scene->events[1]));
     if (stats) stats->ms_render = ms, stats->ms_total = (float)(now_ms() - t0), stats->kernel_launches = launches;
-    cleanup();
-#undef CU2
     return RT_OK;
 }
 

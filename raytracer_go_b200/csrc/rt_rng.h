@@ -19,14 +19,6 @@
 
 #include "rt_math.h"
 
-RT_HD uint32_t rt_mulhi32(uint32_t a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-    return __umulhi(a, b);
-#else
-    return (uint32_t)(((uint64_t)a * b) >> 32);
-#endif
-}
-
 struct RngBlock {
     float u0, u1, u2, u3;
 };
@@ -46,11 +38,12 @@ struct PathRng {
         uint32_t q0 = k0, q1 = k1;
 #pragma unroll
         for (int r = 0; r < 10; r++) {
-            const uint32_t hi0 = rt_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const uint32_t hi1 = rt_mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            const uint32_t n0 = hi1 ^ c1 ^ q0;
-            const uint32_t n2 = hi0 ^ c3 ^ q1;
-            c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+            // one 32x32->64 multiply per half (IMAD.WIDE.U32), high word xor-ed, low word passed on
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+            const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ q0;
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ q1;
+            c0 = n0, c1 = (uint32_t)p1, c2 = n2, c3 = (uint32_t)p0;
             q0 += 0x9E3779B9u;
             q1 += 0xBB67AE85u;
         }

@@ -76,6 +76,25 @@ struct StridedStack {
 
 RT_HD float rt_fmin(float a, float b) { return fminf(a, b); } // NaN-ignoring: a NaN slab never culls
 RT_HD float rt_fmax(float a, float b) { return fmaxf(a, b); }
+// Three-input min/max: one FMNMX3 on sm_100 (PTX max.f32 d,a,b,c); same NaN-ignoring semantics.
+RT_HD float rt_fmin3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+RT_HD float rt_fmax3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
 
 // Reciprocal of a direction component for culling only.  A zero / denormal component would give
 // inf and then inf - inf = NaN inside the fused slab test, so it is replaced by +-1e30: a ray
@@ -96,8 +115,8 @@ RT_HD bool box_test(const F4 &lo, const F4 &hi, V3 inv, V3 noi, float tmin, floa
     float x0 = fmaf(lo.x, inv.x, noi.x), x1 = fmaf(hi.x, inv.x, noi.x);
     float y0 = fmaf(lo.y, inv.y, noi.y), y1 = fmaf(hi.y, inv.y, noi.y);
     float z0 = fmaf(lo.z, inv.z, noi.z), z1 = fmaf(hi.z, inv.z, noi.z);
-    float tn = rt_fmax(rt_fmax(rt_fmin(x0, x1), rt_fmin(y0, y1)), rt_fmax(rt_fmin(z0, z1), tmin));
-    float tf = rt_fmin(rt_fmin(rt_fmax(x0, x1), rt_fmax(y0, y1)), rt_fmin(rt_fmax(z0, z1), tbest));
+    float tn = rt_fmax3(rt_fmin(x0, x1), rt_fmin(y0, y1), rt_fmax(rt_fmin(z0, z1), tmin));
+    float tf = rt_fmin3(rt_fmax(x0, x1), rt_fmax(y0, y1), rt_fmin(rt_fmax(z0, z1), tbest));
     tnear = tn;
     return tn <= tf;
 }

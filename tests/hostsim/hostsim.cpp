@@ -126,3 +126,38 @@ int hs_primary_rays(const rt_camera *cam, uint64_t seed, int32_t sample_offset, 
     return 0;
 }
 }
+
+// Per-segment traversal work of real paths (design exploration: SIMT trip-count statistics).
+// For path p = pixel-major/sample-minor index, writes up to max_seg records (inner iterations,
+// sphere tests, depth) and returns the number written.
+extern "C" int64_t hs_segment_stats(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32_t spp,
+                                    int64_t pixel_begin, int64_t n_pixels, int max_leaf, int32_t *iters,
+                                    int32_t *sph_tests, int32_t *depths, int64_t max_seg) {
+    HostScene s;
+    load(d, max_leaf, 0, &s);
+    DevCamera c = make_dev_camera(*cam);
+    int64_t n = 0;
+    for (int64_t pp = 0; pp < n_pixels; pp++) {
+        int64_t pix = pixel_begin + pp;
+        for (int k = 0; k < spp; k++) {
+            PathRng rng;
+            rng.init(seed, (uint32_t)pix, (uint32_t)k);
+            V3 o, dir;
+            generate_ray(c, rng, (int)(pix % cam->width), (int)(pix / cam->width), o, dir);
+            for (int depth = 0; depth < c.max_depth;) {
+                LocalStack<64> stack;
+                HitRec h;
+                WorkCounters wc{0, 0};
+                trace_closest<LocalStack<64>, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
+                                                    s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, &wc);
+                if (n < max_seg) iters[n] = (int32_t)(wc.box_tests / 2), sph_tests[n] = (int32_t)wc.sphere_tests, depths[n] = depth, n++;
+                if (h.slot == RT_REF_NONE) break;
+                const int mi = s.bvh.meta[h.slot].y;
+                V3 atten, emitted;
+                if (!shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[h.slot], h.t, rng, o, dir, atten, emitted)) break;
+                depth++;
+            }
+        }
+    }
+    return n;
+}
