@@ -202,3 +202,68 @@ def test_errors_are_status_codes(gpu, rtlib):
     assert rc == abi.RT_ERR_INVALID_ARGUMENT and b"material" in rtlib.rt_last_error()
     desc2, keep2 = scenes.random_scene().to_desc()
     assert rtlib.rt_scene_create(C.byref(desc2), 99, C.byref(h)) == abi.RT_ERR_INVALID_ARGUMENT
+
+
+def _splitmix_scene(seed=0x5EED0001):
+    """The scene rt_demo.cpp builds (main.go:240-286 with a SplitMix64 rand.Float32())."""
+    state = [seed]
+
+    def f32():
+        state[0] = (state[0] + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = state[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        z ^= z >> 31
+        return np.float32(z >> 40) * np.float32(1.0 / 16777216.0)
+    F = np.float32
+    w = api.NewWorld()
+    w.Add(api.NewSphere(api.NewVec3(0, -1000, 0), 1000, api.NewLambertian(
+        api.NewCheckered(0.32, api.NewVec3(.2, .3, .1), api.NewVec3(.9, .9, .9)))))
+    for i in range(-11, 11):
+        for j in range(-11, 11):
+            mp = f32()
+            cx = F(i) + F(0.9) * f32()
+            cz = F(j) + F(0.9) * f32()
+            dx, dz = cx - F(4), cz
+            if np.sqrt(np.float64(dx * dx + F(0) + dz * dz)).astype(F) > F(0.9):
+                if mp < F(0.8):
+                    a, b, c, d, e, g = (f32() for _ in range(6))
+                    m = api.NewLambertian(api.NewSolidColor(a * d, b * e, c * g))
+                elif mp < F(0.95):
+                    a, b, c = (F(0.5) + f32() * F(0.5) for _ in range(3))
+                    m = api.NewMetal(api.NewVec3(a, b, c), f32() * F(0.5))
+                else:
+                    m = api.NewDielectric(1.5)
+                w.Add(api.NewSphere(api.NewVec3(cx, 0.2, cz), 0.2, m))
+    w.Add(api.NewSphere(api.NewVec3(0, 1, 0), 1, api.NewDielectric(1.5)))
+    w.Add(api.NewSphere(api.NewVec3(-4, 1, 0), 1, api.NewLambertian(api.NewSolidColor(.4, .2, .1))))
+    w.Add(api.NewSphere(api.NewVec3(4, 1, 0), 1, api.NewMetal(api.NewVec3(.7, .6, .5), 0)))
+    return w
+
+
+def test_host_mirrors_write_the_reference_ppm(gpu, orc, tmp_path):
+    """The C++ mirror (host/rt_demo: main.go's randSpheres against rtgo.hpp) and the Python mirror
+    (api.NewCamera(...).Render) produce the same P3 file, framed as camera.go:183-188/242, and its
+    pixels equal the oracle's render of the flattened world."""
+    import io
+    import os
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "raytracer_go_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host, "rt_demo"])
+    out = tmp_path / "img.ppm"
+    subprocess.check_call([os.path.join(host, "rt_demo"), "160", "3", str(out)])
+    cpp = out.read_text()
+    cam = api.NewCamera(16.0 / 9.0, 160, api.WithSamplesPerPixel(3), api.WithMaxRayDepth(50),
+                        api.WithLookFrom(api.NewVec3(13, 2, 3)), api.WithLookAt(api.NewVec3(0, 0, 0)),
+                        api.WithFOVDegrees(20), api.WithDefocusAngleDegrees(0.6), api.WithFocusDist(10),
+                        api.WithBackgroundColor(api.NewVec3(0.7, 0.8, 1)))
+    world = _splitmix_scene()
+    buf = io.StringIO()
+    assert cam.Render(api.NewBVHFromWorld(world), buf) is None
+    py = buf.getvalue()
+    lines = py.split("\n")
+    assert lines[:3] == ["P3", "160 90", "255"] and lines[-1] == "" and len(lines) == 3 + 160 * 90 + 1
+    assert cpp == py
+    rgb = np.array([[int(v) for v in l.split()] for l in lines[3:-1]], np.uint8).reshape(90, 160, 3)
+    rrgb, _, _ = orc.render(api.flatten_world(world), cam.c, SEED, order=orc.ORDER_ITERATIVE)
+    assert (rgb != rrgb).any(-1).mean() < 1e-3
