@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -47,7 +48,9 @@ struct Builder {
     FlatBvh *out;
     int max_leaf;
 
-    static const int NBINS = 16;
+    static const int NBINS = 64; // upper bound; `nbins` bins are used
+    int nbins = 16;
+    double c_trav = 1.2; // cost of visiting a node pair, in sphere tests
 
     // returns the ref of the subtree over order[b, e), writes its box
     uint32_t build(size_t b, size_t e, uint32_t depth, Box *box_out) {
@@ -71,12 +74,12 @@ struct Builder {
                 if (!(ext > 0)) continue;
                 Box bin_box[NBINS];
                 size_t bin_n[NBINS] = {0};
-                for (int k = 0; k < NBINS; k++) bin_box[k].reset();
-                float scale = (float)NBINS / ext;
+                for (int k = 0; k < nbins; k++) bin_box[k].reset();
+                float scale = (float)nbins / ext;
                 for (size_t i = b; i < e; i++) {
                     const rt_sphere &s = sph[order[i]];
                     float c = axis == 0 ? s.cx : axis == 1 ? s.cy : s.cz;
-                    int k = std::min(NBINS - 1, std::max(0, (int)((c - lo) * scale)));
+                    int k = std::min(nbins - 1, std::max(0, (int)((c - lo) * scale)));
                     bin_box[k].grow(boxes[order[i]]);
                     bin_n[k]++;
                 }
@@ -85,14 +88,14 @@ struct Builder {
                 Box acc;
                 acc.reset();
                 size_t cnt = 0;
-                for (int k = NBINS - 1; k > 0; k--) {
+                for (int k = nbins - 1; k > 0; k--) {
                     acc.grow(bin_box[k]);
                     cnt += bin_n[k];
                     right_area[k] = acc.half_area(), right_n[k] = cnt;
                 }
                 acc.reset();
                 cnt = 0;
-                for (int k = 0; k < NBINS - 1; k++) {
+                for (int k = 0; k < nbins - 1; k++) {
                     acc.grow(bin_box[k]);
                     cnt += bin_n[k];
                     if (cnt == 0 || right_n[k + 1] == 0) continue;
@@ -102,18 +105,18 @@ struct Builder {
             }
         }
         const double parent_area = std::max(bounds.half_area(), 1e-30);
-        const double split_cost = 1.2 + best_cost / parent_area;
+        const double split_cost = c_trav + best_cost / parent_area;
         const bool can_leaf = n <= (size_t)max_leaf;
         if (can_leaf && (best_axis < 0 || (double)n <= split_cost)) return make_leaf(b, e);
 
         size_t mid;
         if (best_axis >= 0) {
             float lo = cb.lo[best_axis], ext = cb.hi[best_axis] - cb.lo[best_axis];
-            float scale = (float)NBINS / ext;
+            float scale = (float)nbins / ext;
             auto it = std::partition(order.begin() + b, order.begin() + e, [&](uint32_t p) {
                 const rt_sphere &s = sph[p];
                 float c = best_axis == 0 ? s.cx : best_axis == 1 ? s.cy : s.cz;
-                int k = std::min(NBINS - 1, std::max(0, (int)((c - lo) * scale)));
+                int k = std::min(nbins - 1, std::max(0, (int)((c - lo) * scale)));
                 return k <= best_bin;
             });
             mid = (size_t)(it - order.begin());
@@ -206,6 +209,8 @@ void build_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, i
     max_leaf = std::max(1, std::min(max_leaf, RT_MAX_LEAF));
     Builder b;
     b.sph = spheres, b.out = out, b.max_leaf = max_leaf;
+    if (const char *e = getenv("RT_B200_BVH_BINS")) b.nbins = std::max(2, std::min(64, atoi(e)));
+    if (const char *e = getenv("RT_B200_BVH_CTRAV")) b.c_trav = atof(e);
     b.boxes.resize(n), b.order.resize(n);
     double m[3], ext;
     compute_scene_center(spheres, n, m, &ext);

@@ -127,7 +127,6 @@ struct RenderParams {
     unsigned int *counter; // next unclaimed path index
     unsigned long long *stats; // rays, hits, box tests, sphere tests
     uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
-    int spec_min;          // speculative traversal: leave the descend loop below this many lanes
 };
 
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 
         // ---- one path segment: ray.go:32-54 unrolled front to back ----
         HitRec h;
-        trace_closest<Stack, COUNT>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, p.spec_min);
+        trace_closest<Stack, COUNT>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc);
         n_rays++;
         bool done;
         if (h.slot == RT_REF_NONE) {
@@ -517,7 +516,7 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ De
         const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         HitRec h;
-        trace_closest<Stack, false>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, 12);
+        trace_closest<Stack, false>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr);
         if (h.slot == RT_REF_NONE) {
             id_out[i] = -1, t_out[i] = 0.0f;
         } else {
@@ -972,7 +971,6 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.counter = s->d_counter;
     p.stats = s->d_stats;
     p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", 8)));
-    p.spec_min = std::min(32, std::max(0, env_int("RT_B200_SPEC_MIN", 12)));
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
         for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {

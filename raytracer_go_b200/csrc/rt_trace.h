@@ -139,62 +139,28 @@ RT_HD bool sphere_candidate(const F4 &s, V3 o, V3 d, float a, float tmin, float 
     return true;
 }
 
-// Running closest hit of one traversal.
-struct Closest {
-    float tbest;
-    uint32_t best_slot;
-};
-
-// Tests the spheres of one leaf against the ray, keeping (smallest accepted root, lowest object id).
-template <bool COUNT>
-RT_HD void test_leaf(uint32_t ref, const F4 *__restrict__ sph, const I2 *__restrict__ meta, V3 o, V3 d, float a,
-                     float tmin, Closest &c, WorkCounters *wc) {
-    const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
-    for (uint32_t s = first; s < first + count; s++) {
-        const F4 sp = sph[s];
-        float t;
-        if (COUNT) wc->sphere_tests += 1;
-        if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
-        if (t < c.tbest) {
-            c.tbest = t, c.best_slot = s;
-        } else if (t == c.tbest && c.best_slot != RT_REF_NONE) {
-            // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
-            if (meta[s].x < meta[c.best_slot].x) c.best_slot = s;
-        }
-    }
-}
-
-// Speculative "while-while" traversal (Aila & Laine 2009): a lane that reaches a leaf postpones it
-// and keeps descending from the next stack entry, so that the lanes of a warp stay in the box-test
-// loop together; it leaves the loop when it meets a second leaf, when its stack is empty, or (warp
-// vote) when only a few lanes are still descending.  The postponed leaf is then tested by all lanes
-// at once.  Visiting nodes before the postponed leaf has tightened tbest only costs extra box tests;
-// the result does not depend on the order (see the header comment).
 template <class Stack, bool COUNT>
 RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sph,
                          const I2 *__restrict__ meta, uint32_t root_ref, V3 o, V3 d, float tmin,
-                         float tmax, Stack &stack, HitRec &hit, WorkCounters *wc, int spec_min_lanes = 0) {
+                         float tmax, Stack &stack, HitRec &hit, WorkCounters *wc) {
     const V3 inv = v3(cull_rcp(d.x), cull_rcp(d.y), cull_rcp(d.z));
     const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
     const float a = lensq(d);
-    Closest c;
-    c.tbest = tmax, c.best_slot = RT_REF_NONE;
+    float tbest = tmax;
+    uint32_t best_slot = RT_REF_NONE;
+    int32_t best_id = 0x7fffffff;
+    bool have_id = false; // best_id is loaded lazily: only exact ties need it
     stack.reset();
     uint32_t ref = root_ref;
-    uint32_t pending = RT_REF_NONE; // postponed leaf
     for (;;) {
-        while (ref != RT_REF_NONE) {
-            if (ref & RT_LEAF) {
-                if (pending != RT_REF_NONE) break; // a second leaf: test the postponed one first
-                pending = ref;
-                ref = stack.pop();
-                continue;
-            }
+        // "while-while": every lane first descends through inner nodes until it holds a leaf (or
+        // nothing), then the lanes test their leaves together.  RT_REF_NONE has the leaf bit set.
+        while (!(ref & RT_LEAF)) {
             const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1];
             const F4 r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
             float tl, tr;
-            const bool hl = box_test(l0, l1, inv, noi, tmin, c.tbest, tl);
-            const bool hr = box_test(r0, r1, inv, noi, tmin, c.tbest, tr);
+            const bool hl = box_test(l0, l1, inv, noi, tmin, tbest, tl);
+            const bool hr = box_test(r0, r1, inv, noi, tmin, tbest, tr);
             if (COUNT) wc->box_tests += 2;
             const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
             if (hl && hr) {
@@ -208,17 +174,27 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
             } else {
                 ref = stack.pop();
             }
-#if defined(__CUDA_ARCH__)
-            // warp vote: few lanes left in this loop and this one already holds a leaf -> go test it
-            if (pending != RT_REF_NONE && __popc(__activemask()) < spec_min_lanes) break;
-#endif
         }
-        if (pending == RT_REF_NONE) break; // nothing postponed: ref is RT_REF_NONE, traversal done
-        test_leaf<COUNT>(pending, sph, meta, o, d, a, tmin, c, wc);
-        pending = RT_REF_NONE;
+        if (ref == RT_REF_NONE) break;
+        const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
+        for (uint32_t s = first; s < first + count; s++) {
+            const F4 sp = sph[s];
+            float t;
+            if (COUNT) wc->sphere_tests += 1;
+            if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
+            if (t < tbest) {
+                tbest = t, best_slot = s, have_id = false;
+            } else if (t == tbest && best_slot != RT_REF_NONE) {
+                // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
+                if (!have_id) best_id = meta[best_slot].x, have_id = true;
+                const int32_t id = meta[s].x;
+                if (id < best_id) best_slot = s, best_id = id;
+            }
+        }
+        ref = stack.pop();
     }
-    hit.t = c.tbest;
-    hit.slot = c.best_slot;
+    hit.t = tbest;
+    hit.slot = best_slot;
 }
 
 #endif // RT_TRACE_H
