@@ -157,7 +157,7 @@ def config_dict(args, cam_opts, scene, world):
     cam_w = cam_opts.image_width
     return {"workload": f"{args.config}: {scene.name} scene, {len(scene.spheres)} spheres, {cam_w} px wide 16:9, "
                         f"{cam_opts.spp} spp/GPU, depth {cam_opts.max_depth}",
-            "spheres": int(len(scene.spheres)), "width": int(cam_w), "spp_per_gpu": int(cam_opts.spp),
+            "spheres": int(len(scene.spheres)), "quads": int(len(scene.quads)), "width": int(cam_w), "spp_per_gpu": int(cam_opts.spp),
             "max_depth": int(cam_opts.max_depth), "parallelism": f"sample-split x{world}" if world > 1 else "single GPU",
             "l2": "per-pass radiance buffer (512 MiB) exceeds L2; the scene is shared-memory resident by design",
             "seed": scenes.RENDER_SEED}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -60,6 +60,15 @@ typedef struct rt_sphere {
     float r;
     uint32_t material; /* index into rt_scene_desc.materials */
 } rt_sphere;
+
+/* hittables.go:138-147 `Quad{Q, u, v, material}`: the parallelogram Q + a*u + b*v, 0 <= a,b <= 1.
+ * w, normal, D and the padded box (hittables.go:149-165) are derived by the library. */
+typedef struct rt_quad {
+    float q[3];
+    float u[3];
+    float v[3];
+    uint32_t material;
+} rt_quad;
 
 typedef struct rt_material {
     uint32_t kind;    /* rt_material_kind                                              */
@@ -102,6 +111,14 @@ typedef struct rt_scene_desc {
      * sphere the reference's float32 Sphere.Hit (hittables.go:96-116) would accept.  0 = derive
      * from the sphere set. */
     float ray_origin_radius;
+    /* Quads (Quad/Box, hittables.go:138-216).  Object IDs: the position of a
+     * hittable in World.hittables (hittables.go:48-53), which World.Hit breaks exact ties by.  When
+     * sphere_ids / quad_ids are NULL, spheres are objects 0..n_spheres-1 and quads follow; otherwise
+     * the two arrays together must be a permutation of 0..n_spheres+n_quads-1. */
+    const rt_quad *quads;
+    uint64_t n_quads;
+    const uint32_t *sphere_ids;
+    const uint32_t *quad_ids;
 } rt_scene_desc;
 
 /* The derived Camera fields of camera.go:23-52 as computed by Camera.init (camera.go:128-166).
@@ -204,8 +221,8 @@ int rt_resolve_device(const float *d_accum, int32_t width, int32_t height, int32
 
 /* Parity hook with World.Hit semantics (hittables.go:55-72) on an arbitrary ray batch:
  * origins/dirs are n*3 float32 (host), interval (tmin, tmax) is open (bvh.go:18-20).
- * id_out[i] = index of the closest sphere in rt_scene_desc.spheres or -1; t_out[i] = its t
- * (unspecified when id is -1). */
+ * id_out[i] = object ID of the closest hittable (for a sphere-only scene: its index in
+ * rt_scene_desc.spheres) or -1; t_out[i] = its t (unspecified when id is -1). */
 int rt_trace(rt_scene *scene, const float *origins, const float *dirs, int64_t n, float tmin,
              float tmax, int32_t *id_out, float *t_out);
 
@@ -222,9 +239,9 @@ int rt_camera_from_options(const rt_camera_options *o, rt_camera *out);
  * Node i is 8 x 32-bit words: min.xyz, ref, max.xyz, 0 — its own box and what it contains.
  * ref of an inner node = index of the first of its two children (children are nodes ref and
  * ref+1, siblings adjacent, parents before children: depth-first order); ref of a leaf =
- * 0x80000000 | first_slot << 3 | (count-1), 1..8 spheres.  root_ref describes the root (whose
- * box is not stored); 0xFFFFFFFF for an empty scene.  slot_ids maps a sphere slot to its index
- * in rt_scene_desc.spheres. */
+ * 0x80000000 | first_slot << 3 | (count-1), 1..8 spheres (0xC0000000 | ... for a leaf of quads, which
+ * have their own slot array).  root_ref describes the root (whose box is not stored); 0xFFFFFFFF
+ * for an empty scene.  slot_ids maps a sphere slot to its object ID. */
 typedef struct rt_bvh_info {
     uint64_t n_nodes;
     uint64_t n_slots;

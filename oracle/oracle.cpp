@@ -276,8 +276,61 @@ inline Aabb sphere_bounds(const rt_sphere &s) {
     return aabb_from_points(add(c, scale(rvec, -1)), add(c, rvec));
 }
 
+// hittables.go:138-147 plus the fields NewQuad derives (hittables.go:149-165)
+struct Quad {
+    V3 Q, u, v, w, normal;
+    float D;
+    uint32_t material;
+    Aabb bbox;
+};
+
+// bvh.go:63-82
+inline Aabb padded_aabb(Aabb a) {
+    const float eps = 0.0001f;
+    if (a.x.max - a.x.min < eps) a.x.min -= eps, a.x.max += eps;
+    if (a.y.max - a.y.min < eps) a.y.min -= eps, a.y.max += eps;
+    if (a.z.max - a.z.min < eps) a.z.min -= eps, a.z.max += eps;
+    return a;
+}
+
+// hittables.go:149-165
+inline Quad new_quad(const rt_quad &q) {
+    Quad r;
+    r.Q = v3(q.q[0], q.q[1], q.q[2]), r.u = v3(q.u[0], q.u[1], q.u[2]), r.v = v3(q.v[0], q.v[1], q.v[2]);
+    V3 n = cross(r.u, r.v);
+    r.normal = unit(n);
+    r.D = dot(r.normal, r.Q);
+    r.w = scale(n, 1 / dot(n, n));
+    r.material = q.material;
+    r.bbox = padded_aabb(aabb_from_points(r.Q, add(add(r.Q, r.u), r.v)));
+    return r;
+}
+
+// hittables.go:167-194
+inline bool quad_hit(const Quad &q, int32_t object, const Ray &r, Interval rt, HitInfo *out) {
+    g_cnt.sphere_tests++;
+    float denom = dot(r.dir, q.normal);
+    if (std::fabs((double)denom) < 1e-8) return false;
+    float t = (q.D - dot(q.normal, r.origin)) / denom;
+    if (!interval_in(rt, t)) return false;
+    V3 intersection = ray_at(r, t);
+    V3 plane_hit = sub(intersection, q.Q);
+    float alpha = dot(q.w, cross(plane_hit, q.v));
+    float beta = dot(q.w, cross(q.u, plane_hit));
+    if (alpha < 0 || 1 < alpha || beta < 0 || 1 < beta) return false; // InPlane, hittables.go:192-194
+    *out = new_hit_info(t, alpha, beta, r.dir, intersection, q.normal, object);
+    return true;
+}
+
+struct Prim {
+    int kind; // 0 sphere, 1 quad
+    uint32_t index;
+};
+
 struct Scene {
     std::vector<rt_sphere> spheres;
+    std::vector<Quad> quads;
+    std::vector<Prim> prims; // World.hittables: position = object ID (hittables.go:48-53)
     std::vector<rt_material> materials;
     std::vector<rt_texture> textures;
     struct Img {
@@ -285,22 +338,47 @@ struct Scene {
         std::vector<uint16_t> px;
     };
     std::vector<Img> images;
+    uint32_t material_of(int32_t object) const {
+        const Prim &p = prims[object];
+        return p.kind == 0 ? spheres[p.index].material : quads[p.index].material;
+    }
+    Aabb bounds_of(int32_t object) const {
+        const Prim &p = prims[object];
+        return p.kind == 0 ? sphere_bounds(spheres[p.index]) : quads[p.index].bbox;
+    }
+    bool hit_prim(int32_t object, const Ray &r, Interval rt, HitInfo *out) const {
+        const Prim &p = prims[object];
+        return p.kind == 0 ? sphere_hit(spheres[p.index], object, r, rt, out) : quad_hit(quads[p.index], object, r, rt, out);
+    }
 };
 
 bool load_scene(const rt_scene_desc *d, Scene *s) {
     if (!d) return false;
     s->spheres.assign(d->spheres, d->spheres + d->n_spheres);
+    for (uint64_t i = 0; i < d->n_quads; i++) s->quads.push_back(new_quad(d->quads[i]));
+    const size_t n = s->spheres.size() + s->quads.size();
+    s->prims.assign(n, Prim{-1, 0});
+    for (size_t i = 0; i < s->spheres.size(); i++) {
+        size_t id = d->sphere_ids ? d->sphere_ids[i] : i;
+        if (id >= n || s->prims[id].kind != -1) return false;
+        s->prims[id] = Prim{0, (uint32_t)i};
+    }
+    for (size_t i = 0; i < s->quads.size(); i++) {
+        size_t id = d->quad_ids ? d->quad_ids[i] : s->spheres.size() + i;
+        if (id >= n || s->prims[id].kind != -1) return false;
+        s->prims[id] = Prim{1, (uint32_t)i};
+    }
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->textures.assign(d->textures, d->textures + d->n_textures);
     for (uint32_t i = 0; i < d->n_images; i++) {
         Scene::Img im;
         im.w = d->images[i].w, im.h = d->images[i].h;
-        size_t n = (size_t)std::max(im.w, 0) * (size_t)std::max(im.h, 0) * 3;
-        im.px.assign(d->images[i].rgb16, d->images[i].rgb16 + n);
+        size_t np = (size_t)std::max(im.w, 0) * (size_t)std::max(im.h, 0) * 3;
+        im.px.assign(d->images[i].rgb16, d->images[i].rgb16 + np);
         s->images.push_back(std::move(im));
     }
-    for (auto &sp : s->spheres)
-        if (sp.material >= s->materials.size()) return false;
+    for (size_t i = 0; i < n; i++)
+        if (s->material_of((int32_t)i) >= s->materials.size()) return false;
     for (auto &m : s->materials)
         if ((m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT) &&
             m.texture >= s->textures.size())
@@ -314,9 +392,9 @@ bool load_scene(const rt_scene_desc *d, Scene *s) {
 inline bool world_hit(const Scene &sc, const Ray &r, Interval rt, HitInfo *out) {
     bool hit_any = false;
     float closest = rt.max;
-    for (size_t i = 0; i < sc.spheres.size(); i++) {
+    for (size_t i = 0; i < sc.prims.size(); i++) {
         HitInfo hi{};
-        if (sphere_hit(sc.spheres[i], (int32_t)i, r, Interval{rt.min, closest}, &hi)) {
+        if (sc.hit_prim((int32_t)i, r, Interval{rt.min, closest}, &hi)) {
             hit_any = true;
             *out = hi;
             closest = hi.t;
@@ -367,9 +445,9 @@ int32_t ref_bvh_build(const Scene &sc, RefBvh &bvh, std::vector<int32_t> prims, 
     Aabb lb, rb;
     if (prims.size() == 1) {
         node.left_prim = node.right_prim = prims[0];
-        lb = rb = sphere_bounds(sc.spheres[prims[0]]);
+        lb = rb = sc.bounds_of(prims[0]);
     } else if (prims.size() == 2) {
-        Aabb b0 = sphere_bounds(sc.spheres[prims[0]]), b1 = sphere_bounds(sc.spheres[prims[1]]);
+        Aabb b0 = sc.bounds_of(prims[0]), b1 = sc.bounds_of(prims[1]);
         if (ref_compare(b0, b1, axis) > 0) {
             node.left_prim = prims[1], node.right_prim = prims[0];
             lb = b1, rb = b0;
@@ -379,7 +457,7 @@ int32_t ref_bvh_build(const Scene &sc, RefBvh &bvh, std::vector<int32_t> prims, 
         }
     } else {
         std::stable_sort(prims.begin(), prims.end(), [&](int32_t p, int32_t q) {
-            return ref_compare(sphere_bounds(sc.spheres[p]), sphere_bounds(sc.spheres[q]), axis) < 0;
+            return ref_compare(sc.bounds_of(p), sc.bounds_of(q), axis) < 0;
         });
         size_t mid = prims.size() / 2;
         std::vector<int32_t> l(prims.begin(), prims.begin() + mid), r(prims.begin() + mid, prims.end());
@@ -400,11 +478,11 @@ bool ref_bvh_hit(const Scene &sc, const RefBvh &bvh, int32_t n, const Ray &r, In
     if (!aabb_hit(b.box, r, rt)) return false;
     HitInfo lh{}, rh{};
     bool hit_left = b.left_node >= 0 ? ref_bvh_hit(sc, bvh, b.left_node, r, rt, &lh)
-                                     : sphere_hit(sc.spheres[b.left_prim], b.left_prim, r, rt, &lh);
+                                     : sc.hit_prim(b.left_prim, r, rt, &lh);
     Interval right_rt = rt;
     if (hit_left) right_rt.max = lh.t;
     bool hit_right = b.right_node >= 0 ? ref_bvh_hit(sc, bvh, b.right_node, r, right_rt, &rh)
-                                       : sphere_hit(sc.spheres[b.right_prim], b.right_prim, r, right_rt, &rh);
+                                       : sc.hit_prim(b.right_prim, r, right_rt, &rh);
     if (hit_left && hit_right) {
         *out = lh.t < rh.t ? lh : rh;
         return true;
@@ -543,7 +621,7 @@ V3 get_color_recursive(const World &w, const Ray &r, V3 background, int max_dept
     HitInfo hi{};
     if (w.hit(r, Interval{T_MIN, std::numeric_limits<float>::infinity()}, &hi)) {
         g_cnt.hits++;
-        const rt_material &m = w.sc->materials[w.sc->spheres[hi.object].material];
+        const rt_material &m = w.sc->materials[w.sc->material_of(hi.object)];
         V3 emitted = material_emit(*w.sc, m, hi);
         Scatter sc;
         if (!material_scatter(*w.sc, m, r, hi, rng, &sc)) return emitted;
@@ -565,7 +643,7 @@ V3 get_color_iterative(const World &w, Ray r, V3 background, int max_depth, Rng 
         if (!w.hit(r, Interval{T_MIN, std::numeric_limits<float>::infinity()}, &hi))
             return add(radiance, mul(throughput, background));
         g_cnt.hits++;
-        const rt_material &m = w.sc->materials[w.sc->spheres[hi.object].material];
+        const rt_material &m = w.sc->materials[w.sc->material_of(hi.object)];
         V3 emitted = material_emit(*w.sc, m, hi);
         radiance = add(radiance, mul(throughput, emitted));
         Scatter sc;
@@ -694,8 +772,8 @@ int orc_trace(const rt_scene_desc *desc, int mode, uint64_t bvh_seed, const floa
     Scene sc;
     if (!load_scene(desc, &sc)) return -1;
     RefBvh bvh;
-    if (mode == MODE_REF_BVH && !sc.spheres.empty()) {
-        std::vector<int32_t> prims(sc.spheres.size());
+    if (mode == MODE_REF_BVH && !sc.prims.empty()) {
+        std::vector<int32_t> prims(sc.prims.size());
         for (size_t i = 0; i < prims.size(); i++) prims[i] = (int32_t)i;
         SplitMix rng{bvh_seed};
         bvh.root = ref_bvh_build(sc, bvh, prims, rng);
@@ -782,7 +860,7 @@ int orc_scatter(const rt_scene_desc *desc, const float *origin, const float *dir
     if (!world_hit(sc, r, Interval{T_MIN, std::numeric_limits<float>::infinity()}, &hi)) return 1;
     Rng rng(seed, pixel, sample);
     Scatter s{};
-    bool ok = material_scatter(sc, sc.materials[sc.spheres[hi.object].material], r, hi, rng, &s);
+    bool ok = material_scatter(sc, sc.materials[sc.material_of(hi.object)], r, hi, rng, &s);
     float v[10] = {ok ? 1.0f : 0.0f, s.ray.origin.x, s.ray.origin.y, s.ray.origin.z, s.ray.dir.x,
                    s.ray.dir.y, s.ray.dir.z, s.attenuation.x, s.attenuation.y, s.attenuation.z};
     memcpy(out10, v, sizeof v);
@@ -819,8 +897,8 @@ int orc_render(const rt_scene_desc *desc, const rt_camera *cam, uint64_t seed, i
     Scene sc;
     if (!cam || !load_scene(desc, &sc)) return -1;
     RefBvh bvh;
-    if (mode == MODE_REF_BVH && !sc.spheres.empty()) {
-        std::vector<int32_t> prims(sc.spheres.size());
+    if (mode == MODE_REF_BVH && !sc.prims.empty()) {
+        std::vector<int32_t> prims(sc.prims.size());
         for (size_t i = 0; i < prims.size(); i++) prims[i] = (int32_t)i;
         SplitMix rng{bvh_seed};
         bvh.root = ref_bvh_build(sc, bvh, prims, rng);

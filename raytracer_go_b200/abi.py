@@ -5,7 +5,7 @@ sizes/offsets against the compiled library's view where that is observable.
 """
 import ctypes as C
 
-RT_B200_ABI_VERSION = 1
+RT_B200_ABI_VERSION = 2
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1
@@ -28,6 +28,10 @@ class rt_sphere(C.Structure):
                 ("material", C.c_uint32)]
 
 
+class rt_quad(C.Structure):
+    _fields_ = [("q", _f3), ("u", _f3), ("v", _f3), ("material", C.c_uint32)]
+
+
 class rt_material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("albedo", _f3), ("fuzz", C.c_float), ("ior", C.c_float),
                 ("texture", C.c_uint32)]
@@ -48,7 +52,9 @@ class rt_scene_desc(C.Structure):
                 ("materials", C.POINTER(rt_material)), ("n_materials", C.c_uint32),
                 ("textures", C.POINTER(rt_texture)), ("n_textures", C.c_uint32),
                 ("images", C.POINTER(rt_image)), ("n_images", C.c_uint32),
-                ("ray_origin_radius", C.c_float)]
+                ("ray_origin_radius", C.c_float),
+                ("quads", C.POINTER(rt_quad)), ("n_quads", C.c_uint64),
+                ("sphere_ids", C.POINTER(C.c_uint32)), ("quad_ids", C.POINTER(C.c_uint32))]
 
 
 class rt_camera(C.Structure):

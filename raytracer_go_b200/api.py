@@ -206,12 +206,38 @@ def NewSphere(center, radius, mat):
     return Sphere(center, radius, mat)
 
 
+class Quad:  # hittables.go:138-165
+    def __init__(self, Q, u, v, material):
+        self.Q, self.u, self.v, self.material = Q, u, v, material
+
+
+def NewQuad(Q, u, v, material):
+    return Quad(Q, u, v, material)
+
+
+def Box(a, b, mat):
+    """hittables.go:200-216: the six quads of an axis-aligned box, in the reference's order."""
+    mn = tuple(min(F(x), F(y)) for x, y in zip(a, b))
+    mx = tuple(max(F(x), F(y)) for x, y in zip(a, b))
+    dx, dy, dz = NewVec3(mx[0] - mn[0], 0, 0), NewVec3(0, mx[1] - mn[1], 0), NewVec3(0, 0, mx[2] - mn[2])
+    neg = lambda v: tuple(F(-1) * c for c in v)  # noqa: E731  Scale(v, -1)
+    return [
+        NewQuad(NewVec3(mn[0], mn[1], mx[2]), dx, dy, mat),
+        NewQuad(NewVec3(mx[0], mn[1], mx[2]), neg(dz), dy, mat),
+        NewQuad(NewVec3(mx[0], mn[1], mn[2]), neg(dx), dy, mat),
+        NewQuad(NewVec3(mn[0], mn[1], mn[2]), dz, dy, mat),
+        NewQuad(NewVec3(mn[0], mx[1], mx[2]), dx, neg(dz), mat),
+        NewQuad(NewVec3(mn[0], mn[1], mn[2]), dx, dz, mat),
+    ]
+
+
 class World:  # hittables.go:39-53
     def __init__(self):
         self.hittables = []
 
     def Add(self, *hittables):
-        self.hittables.extend(hittables)
+        for h in hittables:  # world.Add(internal.Box(...)...) spreads a slice in Go (main.go:220)
+            self.hittables.extend(h if isinstance(h, (list, tuple)) else [h])
 
 
 def NewWorld():
@@ -236,7 +262,7 @@ def flatten_world(world):
     insertion order.  This is the walk the cgo bridge performs."""
     tex_index, mat_index = {}, {}
     textures, materials, images = [], [], []
-    spheres = np.zeros(len(world.hittables), scenes.SPHERE_DT)
+    spheres, quads, sphere_ids, quad_ids = [], [], [], []
 
     def tex_id(t):
         if id(t) in tex_index:
@@ -273,12 +299,20 @@ def flatten_world(world):
         mat_index[id(m)] = len(materials) - 1
         return mat_index[id(m)]
 
-    for k, h in enumerate(world.hittables):
-        if not isinstance(h, Sphere):
+    for k, h in enumerate(world.hittables):  # k = object ID (hittables.go:48-53)
+        if isinstance(h, Sphere):
+            spheres.append((h.Center[0], h.Center[1], h.Center[2], h.Radius, mat_id(h.Material)))
+            sphere_ids.append(k)
+        elif isinstance(h, Quad):
+            quads.append((h.Q, h.u, h.v, mat_id(h.material)))
+            quad_ids.append(k)
+        else:
             raise TypeError(f"hittable {type(h).__name__} is outside the accelerated path (SURVEY §8f)")
-        spheres[k] = (h.Center[0], h.Center[1], h.Center[2], h.Radius, mat_id(h.Material))
-    return scenes.SceneData(spheres, np.array(materials, scenes.MATERIAL_DT).reshape(-1),
-                            np.array(textures, scenes.TEXTURE_DT).reshape(-1), images)
+    return scenes.SceneData(np.array(spheres, scenes.SPHERE_DT).reshape(-1),
+                            np.array(materials, scenes.MATERIAL_DT).reshape(-1),
+                            np.array(textures, scenes.TEXTURE_DT).reshape(-1), images,
+                            quads=np.array(quads, scenes.QUAD_DT).reshape(-1),
+                            sphere_ids=sphere_ids, quad_ids=quad_ids)
 
 
 # CameraOpt functional options, camera.go:54-102

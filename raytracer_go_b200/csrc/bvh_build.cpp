@@ -2,7 +2,7 @@
 // splits on a random axis at the median of a descending sort; its topology differs on every run
 // and is not part of the result, so this build is free to be a binned-SAH tree.  What must hold
 // is that traversal returns World.Hit's answer (hittables.go:55-72), which needs box culling that
-// can never reject a sphere the reference's float32 Sphere.Hit (hittables.go:96-116) accepts.
+// can never reject a primitive the reference's float32 Hit (hittables.go:96-116, 167-190) accepts.
 //
 // Box padding.  With u = 2^-24, the float32 discriminant hittables.go:97-102 carries an absolute
 // error of at most ~20 u |d|^2 |o-c|^2, so the reference can accept a root for a ray that
@@ -10,7 +10,9 @@
 // point then lies within r + delta of the centre.  Each sphere's box is therefore grown by
 //   pad = K u D^2 / (2 r) + 8 u (D + |m| + |c| + r),   K = 24,
 // where D bounds |o - c| for every ray origin o within `origin_radius` of the scene's median
-// centre m (the second term covers the fused slab test's own rounding).  rt_render / rt_trace
+// centre m (the second term covers the fused slab test's own rounding).  A quad's accepted point
+// is within a few ulp of its plane and of its edges: its box (the reference's padded box,
+// hittables.go:161 / bvh.go:63-82) is grown by 32 u (D + |Q| + |u| + |v|).  rt_render / rt_trace
 // enlarge origin_radius (refit, no rebuild) when a camera or a ray batch lies outside it.
 #include "bvh_build.h"
 #include "rt_shade.h"
@@ -40,32 +42,105 @@ struct Box {
 
 const double U = 1.0 / 16777216.0; // 2^-24
 const double K_DISC = 24.0;
+const float NEG_INF = -std::numeric_limits<float>::infinity(), POS_INF = std::numeric_limits<float>::infinity();
+
+// global primitive index g: [0, n_spheres) spheres, then quads
+inline bool is_quad(const ScenePrims &p, uint32_t g) { return g >= p.spheres.size(); }
+
+void prim_center(const ScenePrims &p, uint32_t g, double c[3], double *extent) {
+    if (!is_quad(p, g)) {
+        const rt_sphere &s = p.spheres[g];
+        c[0] = s.cx, c[1] = s.cy, c[2] = s.cz;
+        *extent = std::fabs((double)s.r);
+    } else {
+        const rt_quad &q = p.quads[g - p.spheres.size()];
+        double e = 0;
+        for (int k = 0; k < 3; k++) {
+            c[k] = q.q[k] + 0.5 * ((double)q.u[k] + q.v[k]);
+            e += 0.25 * ((double)q.u[k] + q.v[k]) * ((double)q.u[k] + q.v[k]);
+        }
+        double e2 = 0;
+        for (int k = 0; k < 3; k++) e2 += 0.25 * ((double)q.u[k] - q.v[k]) * ((double)q.u[k] - q.v[k]);
+        *extent = std::sqrt(std::max(e, e2));
+    }
+}
+
+// Padded box of one primitive for ray origins within origin_radius of m.
+Box padded_box(const ScenePrims &p, uint32_t g, const double m[3], double origin_radius, float *pad_out) {
+    double c[3], ext;
+    prim_center(p, g, c, &ext);
+    const double dx = c[0] - m[0], dy = c[1] - m[1], dz = c[2] - m[2];
+    const double D = origin_radius + std::sqrt(dx * dx + dy * dy + dz * dz);
+    const double cmax = std::max(std::fabs(c[0]), std::max(std::fabs(c[1]), std::fabs(c[2])));
+    const double mmax = std::max(std::fabs(m[0]), std::max(std::fabs(m[1]), std::fabs(m[2])));
+    Box b;
+    double pad;
+    if (!is_quad(p, g)) {
+        const rt_sphere &s = p.spheres[g];
+        const double r = std::fabs((double)s.r);
+        pad = K_DISC * U * D * D / (2.0 * std::max(r, 1e-30)) + 8.0 * U * (D + mmax + cmax + r);
+        pad = std::min(pad, D + r); // a box as large as the whole origin region is always enough
+        const float cc[3] = {s.cx, s.cy, s.cz};
+        for (int k = 0; k < 3; k++) {
+            b.lo[k] = std::nextafter((float)((double)cc[k] - r - pad), NEG_INF);
+            b.hi[k] = std::nextafter((float)((double)cc[k] + r + pad), POS_INF);
+        }
+    } else {
+        const rt_quad &q = p.quads[g - p.spheres.size()];
+        pad = 32.0 * U * (D + mmax + cmax + 2 * ext) + 1e-4; // >= the reference's own 1e-4 thin-box padding
+        for (int k = 0; k < 3; k++) {
+            const double a = q.q[k], e = (double)q.q[k] + q.u[k] + q.v[k];
+            const double lo = std::min(std::min(a, e), std::min(a + q.u[k], a + q.v[k]));
+            const double hi = std::max(std::max(a, e), std::max(a + q.u[k], a + q.v[k]));
+            b.lo[k] = std::nextafter((float)(lo - pad), NEG_INF);
+            b.hi[k] = std::nextafter((float)(hi + pad), POS_INF);
+        }
+    }
+    *pad_out = (float)pad;
+    return b;
+}
+
+// Device record of a quad: the fields NewQuad derives (hittables.go:149-165), float32, unfused.
+void write_quad(const rt_quad &q, uint32_t id, F4 *out) {
+    const V3 Q = v3(q.q[0], q.q[1], q.q[2]), u = v3(q.u[0], q.u[1], q.u[2]), v = v3(q.v[0], q.v[1], q.v[2]);
+    const V3 n = v3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x); // Cross(u, v)
+    const V3 normal = unit(n);
+    const float D = dot(normal, Q);
+    const V3 w = n * (1 / dot(n, n));
+    out[0].x = Q.x, out[0].y = Q.y, out[0].z = Q.z, out[0].w = D;
+    out[1].x = u.x, out[1].y = u.y, out[1].z = u.z, out[1].w = as_float(q.material);
+    out[2].x = v.x, out[2].y = v.y, out[2].z = v.z, out[2].w = as_float(id);
+    out[3].x = w.x, out[3].y = w.y, out[3].z = w.z, out[3].w = 0;
+    out[4].x = normal.x, out[4].y = normal.y, out[4].z = normal.z, out[4].w = 0;
+}
 
 struct Builder {
-    const rt_sphere *sph;
-    std::vector<Box> boxes;      // padded per-sphere boxes
+    const ScenePrims *prims;
+    std::vector<Box> boxes;      // padded per-primitive boxes
+    std::vector<float> cent;     // 3 per primitive
     std::vector<uint32_t> order; // permutation being partitioned
     FlatBvh *out;
     int max_leaf;
 
     static const int NBINS = 64; // upper bound; `nbins` bins are used
     int nbins = 16;
-    double c_trav = 1.2; // cost of visiting a node pair, in sphere tests
+    double c_trav = 1.2; // cost of visiting a node pair, in primitive tests
 
     // returns the ref of the subtree over order[b, e), writes its box
     uint32_t build(size_t b, size_t e, uint32_t depth, Box *box_out) {
         Box bounds, cb;
         bounds.reset(), cb.reset();
+        bool any_quad = false, any_sphere = false;
         for (size_t i = b; i < e; i++) {
-            const Box &bx = boxes[order[i]];
-            bounds.grow(bx);
-            const rt_sphere &s = sph[order[i]];
-            float c[3] = {s.cx, s.cy, s.cz};
-            for (int k = 0; k < 3; k++) cb.lo[k] = std::min(cb.lo[k], c[k]), cb.hi[k] = std::max(cb.hi[k], c[k]);
+            const uint32_t g = order[i];
+            bounds.grow(boxes[g]);
+            (is_quad(*prims, g) ? any_quad : any_sphere) = true;
+            for (int k = 0; k < 3; k++)
+                cb.lo[k] = std::min(cb.lo[k], cent[3 * g + k]), cb.hi[k] = std::max(cb.hi[k], cent[3 * g + k]);
         }
         *box_out = bounds;
         const size_t n = e - b;
-        // SAH over 16 centroid bins per axis; cost unit = one sphere test, a box pair costs 1.2
+        // SAH over centroid bins per axis; cost unit = one primitive test
         double best_cost = std::numeric_limits<double>::infinity();
         int best_axis = -1, best_bin = -1;
         if (n > 1) {
@@ -77,10 +152,9 @@ struct Builder {
                 for (int k = 0; k < nbins; k++) bin_box[k].reset();
                 float scale = (float)nbins / ext;
                 for (size_t i = b; i < e; i++) {
-                    const rt_sphere &s = sph[order[i]];
-                    float c = axis == 0 ? s.cx : axis == 1 ? s.cy : s.cz;
-                    int k = std::min(nbins - 1, std::max(0, (int)((c - lo) * scale)));
-                    bin_box[k].grow(boxes[order[i]]);
+                    const uint32_t g = order[i];
+                    int k = std::min(nbins - 1, std::max(0, (int)((cent[3 * g + axis] - lo) * scale)));
+                    bin_box[k].grow(boxes[g]);
                     bin_n[k]++;
                 }
                 double right_area[NBINS];
@@ -106,19 +180,21 @@ struct Builder {
         }
         const double parent_area = std::max(bounds.half_area(), 1e-30);
         const double split_cost = c_trav + best_cost / parent_area;
-        const bool can_leaf = n <= (size_t)max_leaf;
+        // a leaf holds primitives of one kind; quads are one per leaf (80-byte records)
+        const bool can_leaf = !(any_quad && any_sphere) && n <= (size_t)(any_quad ? 1 : max_leaf);
         if (can_leaf && (best_axis < 0 || (double)n <= split_cost)) return make_leaf(b, e);
 
         size_t mid;
         if (best_axis >= 0) {
             float lo = cb.lo[best_axis], ext = cb.hi[best_axis] - cb.lo[best_axis];
             float scale = (float)nbins / ext;
-            auto it = std::partition(order.begin() + b, order.begin() + e, [&](uint32_t p) {
-                const rt_sphere &s = sph[p];
-                float c = best_axis == 0 ? s.cx : best_axis == 1 ? s.cy : s.cz;
-                int k = std::min(nbins - 1, std::max(0, (int)((c - lo) * scale)));
+            auto it = std::partition(order.begin() + b, order.begin() + e, [&](uint32_t g) {
+                int k = std::min(nbins - 1, std::max(0, (int)((cent[3 * g + best_axis] - lo) * scale)));
                 return k <= best_bin;
             });
+            mid = (size_t)(it - order.begin());
+        } else if (any_quad && any_sphere) {
+            auto it = std::partition(order.begin() + b, order.begin() + e, [&](uint32_t g) { return !is_quad(*prims, g); });
             mid = (size_t)(it - order.begin());
         } else {
             mid = b + n / 2; // coincident centres: split by count
@@ -146,17 +222,29 @@ struct Builder {
     }
 
     uint32_t make_leaf(size_t b, size_t e) {
+        const ScenePrims &p = *prims;
+        if (is_quad(p, order[b])) {
+            const uint32_t first = (uint32_t)out->quad_prim.size();
+            for (size_t i = b; i < e; i++) {
+                const uint32_t qi = order[i] - (uint32_t)p.spheres.size();
+                out->quad.resize(out->quad.size() + RT_QUAD_F4);
+                write_quad(p.quads[qi], p.quad_ids[qi], &out->quad[(size_t)RT_QUAD_F4 * out->quad_prim.size()]);
+                out->quad_prim.push_back(qi);
+            }
+            return RT_LEAF | RT_LEAF_QUAD | (first << 3) | (uint32_t)(e - b - 1);
+        }
         const uint32_t first = (uint32_t)out->sph.size();
-        // keep object order inside a leaf: ties inside one leaf then resolve without a meta load
-        std::sort(order.begin() + b, order.begin() + e);
+        // ascending object ID inside a leaf
+        std::sort(order.begin() + b, order.begin() + e, [&](uint32_t x, uint32_t y) { return p.sphere_ids[x] < p.sphere_ids[y]; });
         for (size_t i = b; i < e; i++) {
-            const rt_sphere &s = sph[order[i]];
+            const rt_sphere &s = p.spheres[order[i]];
             F4 f;
             f.x = s.cx, f.y = s.cy, f.z = s.cz, f.w = s.r;
             out->sph.push_back(f);
             I2 m;
-            m.x = (int32_t)order[i], m.y = (int32_t)s.material;
+            m.x = (int32_t)p.sphere_ids[order[i]], m.y = (int32_t)s.material;
             out->meta.push_back(m);
+            out->sph_prim.push_back(order[i]);
         }
         return RT_LEAF | (first << 3) | (uint32_t)(e - b - 1);
     }
@@ -164,77 +252,81 @@ struct Builder {
 
 } // namespace
 
-void compute_scene_center(const rt_sphere *spheres, uint64_t n, double m[3], double *extent90) {
+bool load_scene_prims(const rt_scene_desc *d, ScenePrims *out) {
+    out->spheres.assign(d->spheres, d->spheres + d->n_spheres);
+    out->quads.assign(d->quads, d->quads + d->n_quads);
+    const size_t ns = out->spheres.size(), nq = out->quads.size(), n = ns + nq;
+    out->sphere_ids.resize(ns), out->quad_ids.resize(nq);
+    for (size_t i = 0; i < ns; i++) out->sphere_ids[i] = d->sphere_ids ? d->sphere_ids[i] : (uint32_t)i;
+    for (size_t i = 0; i < nq; i++) out->quad_ids[i] = d->quad_ids ? d->quad_ids[i] : (uint32_t)(ns + i);
+    if (d->sphere_ids || d->quad_ids) { // must be a permutation of 0..n-1
+        std::vector<bool> seen(n, false);
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t id = i < ns ? out->sphere_ids[i] : out->quad_ids[i - ns];
+            if (id >= n || seen[id]) return false;
+            seen[id] = true;
+        }
+    }
+    return true;
+}
+
+void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90) {
     m[0] = m[1] = m[2] = 0, *extent90 = 0;
+    const size_t n = prims.size();
     if (n == 0) return;
     std::vector<float> v(n);
+    std::vector<double> c(3 * n), ext(n);
+    for (size_t g = 0; g < n; g++) prim_center(prims, (uint32_t)g, &c[3 * g], &ext[g]);
     for (int k = 0; k < 3; k++) {
-        for (uint64_t i = 0; i < n; i++) v[i] = k == 0 ? spheres[i].cx : k == 1 ? spheres[i].cy : spheres[i].cz;
+        for (size_t g = 0; g < n; g++) v[g] = (float)c[3 * g + k];
         std::nth_element(v.begin(), v.begin() + n / 2, v.end());
         m[k] = v[n / 2];
     }
-    for (uint64_t i = 0; i < n; i++) {
-        double dx = spheres[i].cx - m[0], dy = spheres[i].cy - m[1], dz = spheres[i].cz - m[2];
-        v[i] = (float)(std::sqrt(dx * dx + dy * dy + dz * dz) + std::fabs((double)spheres[i].r));
+    for (size_t g = 0; g < n; g++) {
+        double dx = c[3 * g] - m[0], dy = c[3 * g + 1] - m[1], dz = c[3 * g + 2] - m[2];
+        v[g] = (float)(std::sqrt(dx * dx + dy * dy + dz * dz) + ext[g]);
     }
     size_t k90 = (size_t)((n - 1) * 0.9);
     std::nth_element(v.begin(), v.begin() + k90, v.end());
     *extent90 = v[k90];
 }
 
-// Padded box of one sphere for ray origins within origin_radius of m.
-static Box padded_box(const rt_sphere &s, const double m[3], double origin_radius, float *pad_out) {
-    double r = std::fabs((double)s.r);
-    double dx = s.cx - m[0], dy = s.cy - m[1], dz = s.cz - m[2];
-    double D = origin_radius + std::sqrt(dx * dx + dy * dy + dz * dz);
-    double cmax = std::max(std::fabs((double)s.cx), std::max(std::fabs((double)s.cy), std::fabs((double)s.cz)));
-    double mmax = std::max(std::fabs(m[0]), std::max(std::fabs(m[1]), std::fabs(m[2])));
-    double pad = K_DISC * U * D * D / (2.0 * std::max(r, 1e-30)) + 8.0 * U * (D + mmax + cmax + r);
-    pad = std::min(pad, D + r); // a box as large as the whole origin region is always enough
-    Box b;
-    const float c[3] = {s.cx, s.cy, s.cz};
-    for (int k = 0; k < 3; k++) {
-        b.lo[k] = std::nextafter((float)((double)c[k] - r - pad), -std::numeric_limits<float>::infinity());
-        b.hi[k] = std::nextafter((float)((double)c[k] + r + pad), std::numeric_limits<float>::infinity());
-    }
-    *pad_out = (float)pad;
-    return b;
-}
-
-void build_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, int max_leaf, FlatBvh *out) {
-    out->nodes.clear(), out->sph.clear(), out->meta.clear();
-    out->root_ref = RT_REF_NONE, out->max_depth = 0;
-    out->pad_min = out->pad_max = 0;
+void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out) {
+    *out = FlatBvh();
+    const size_t n = prims.size();
     if (n == 0) return;
     max_leaf = std::max(1, std::min(max_leaf, RT_MAX_LEAF));
     Builder b;
-    b.sph = spheres, b.out = out, b.max_leaf = max_leaf;
+    b.prims = &prims, b.out = out, b.max_leaf = max_leaf;
     if (const char *e = getenv("RT_B200_BVH_BINS")) b.nbins = std::max(2, std::min(64, atoi(e)));
     if (const char *e = getenv("RT_B200_BVH_CTRAV")) b.c_trav = atof(e);
-    b.boxes.resize(n), b.order.resize(n);
+    b.boxes.resize(n), b.order.resize(n), b.cent.resize(3 * n);
     double m[3], ext;
-    compute_scene_center(spheres, n, m, &ext);
-    float pmin = std::numeric_limits<float>::infinity(), pmax = 0;
-    for (uint64_t i = 0; i < n; i++) {
+    compute_scene_center(prims, m, &ext);
+    float pmin = POS_INF, pmax = 0;
+    for (size_t g = 0; g < n; g++) {
         float pad;
-        b.boxes[i] = padded_box(spheres[i], m, origin_radius, &pad);
+        b.boxes[g] = padded_box(prims, (uint32_t)g, m, origin_radius, &pad);
         pmin = std::min(pmin, pad), pmax = std::max(pmax, pad);
-        b.order[i] = (uint32_t)i;
+        double c[3], e;
+        prim_center(prims, (uint32_t)g, c, &e);
+        b.cent[3 * g] = (float)c[0], b.cent[3 * g + 1] = (float)c[1], b.cent[3 * g + 2] = (float)c[2];
+        b.order[g] = (uint32_t)g;
     }
     out->pad_min = pmin, out->pad_max = pmax;
     out->nodes.reserve(4 * n);
-    out->sph.reserve(n), out->meta.reserve(n);
+    out->sph.reserve(prims.spheres.size()), out->meta.reserve(prims.spheres.size());
     Box root_box;
     out->root_ref = b.build(0, n, 0, &root_box);
 }
 
 // Recompute every box for a larger origin_radius, topology unchanged.  Nodes are in pre-order
 // (children after parents), so one reverse sweep rebuilds parents from children.
-void refit_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, FlatBvh *bvh) {
-    if (n == 0 || bvh->root_ref == RT_REF_NONE) return;
+void refit_flat_bvh(const ScenePrims &prims, float origin_radius, FlatBvh *bvh) {
+    if (prims.size() == 0 || bvh->root_ref == RT_REF_NONE) return;
     double m[3], ext;
-    compute_scene_center(spheres, n, m, &ext);
-    float pmin = std::numeric_limits<float>::infinity(), pmax = 0;
+    compute_scene_center(prims, m, &ext);
+    float pmin = POS_INF, pmax = 0;
     const size_t n_nodes = bvh->nodes.size() / 2;
     for (size_t ii = n_nodes; ii-- > 0;) {
         uint32_t ref;
@@ -242,10 +334,12 @@ void refit_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, F
         Box bx;
         bx.reset();
         if (ref & RT_LEAF) {
-            uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
+            const bool quad = (ref & RT_LEAF_QUAD) != 0;
+            uint32_t first = (ref & RT_LEAF_SLOT_MASK) >> 3, count = (ref & 7u) + 1;
             for (uint32_t s = first; s < first + count; s++) {
                 float pad;
-                bx.grow(padded_box(spheres[bvh->meta[s].x], m, origin_radius, &pad));
+                const uint32_t g = quad ? (uint32_t)prims.spheres.size() + bvh->quad_prim[s] : bvh->sph_prim[s];
+                bx.grow(padded_box(prims, g, m, origin_radius, &pad));
                 pmin = std::min(pmin, pad), pmax = std::max(pmax, pad);
             }
         } else {
@@ -264,7 +358,6 @@ void refit_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, F
     bvh->pad_min = pmin, bvh->pad_max = pmax;
 }
 
-// Fold textures into 32-byte device material records (layout in rt_shade.h).
 void pack_materials(const rt_scene_desc *d, std::vector<F4> *out) {
     out->resize(2 * (size_t)d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; i++) {

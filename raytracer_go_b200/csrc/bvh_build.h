@@ -8,23 +8,36 @@
 #include "../../include/rt_b200.h"
 #include "rt_trace.h"
 
+// Host copy of the scene's hittables (World.hittables split by kind, with their object IDs).
+struct ScenePrims {
+    std::vector<rt_sphere> spheres;
+    std::vector<uint32_t> sphere_ids;
+    std::vector<rt_quad> quads;
+    std::vector<uint32_t> quad_ids;
+    size_t size() const { return spheres.size() + quads.size(); }
+};
+
 struct FlatBvh {
     std::vector<F4> nodes;          // 2 x F4 per node, siblings adjacent, depth-first order
-    std::vector<F4> sph;            // per slot: centre, radius
-    std::vector<I2> meta;           // per slot: object index, material index
+    std::vector<F4> sph;            // per sphere slot: centre, radius
+    std::vector<I2> meta;           // per sphere slot: object ID, material index
+    std::vector<uint32_t> sph_prim; // per sphere slot: index into ScenePrims.spheres
+    std::vector<F4> quad;           // per quad slot: RT_QUAD_F4 x F4 (layout in rt_trace.h)
+    std::vector<uint32_t> quad_prim; // per quad slot: index into ScenePrims.quads
     uint32_t root_ref = RT_REF_NONE;
     uint32_t max_depth = 0;         // deepest chain of inner nodes (bounds the traversal stack)
-    float pad_min = 0, pad_max = 0; // smallest / largest box padding applied to a sphere
+    float pad_min = 0, pad_max = 0; // smallest / largest box padding applied to a primitive
 };
 
 // max_leaf in [1, RT_MAX_LEAF].  origin_radius: rt_scene_desc.ray_origin_radius (0 = derive).
-void build_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, int max_leaf, FlatBvh *out);
+void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out);
 // Recompute all boxes for a (larger) origin radius; topology and slot order are unchanged.
-void refit_flat_bvh(const rt_sphere *spheres, uint64_t n, float origin_radius, FlatBvh *bvh);
-// Per-axis median of the sphere centres and the 90th percentile of |c - m| + r.
-void compute_scene_center(const rt_sphere *spheres, uint64_t n, double m[3], double *extent90);
-
+void refit_flat_bvh(const ScenePrims &prims, float origin_radius, FlatBvh *bvh);
+// Per-axis median of the primitive centres and the 90th percentile of |c - m| + extent.
+void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90);
 // Fold each material's texture into its 32-byte device record (layout in rt_shade.h).
 void pack_materials(const rt_scene_desc *d, std::vector<F4> *out);
+// Copies (and validates the IDs of) the hittables of a scene description; false = bad IDs.
+bool load_scene_prims(const rt_scene_desc *d, ScenePrims *out);
 
 #endif

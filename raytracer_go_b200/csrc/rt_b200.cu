@@ -67,19 +67,21 @@ struct DevScene {
     const I2 *meta;
     const F4 *mats;
     const DevImage *images;
-    uint32_t root_ref, n_nodes, n_slots, n_mats;
+    const F4 *quads; // RT_QUAD_F4 x F4 per quad slot
+    uint32_t root_ref, n_nodes, n_slots, n_mats, n_quad_slots;
     uint32_t stack_depth; // entries per thread for the shared-memory stack
 };
 
 static size_t scene_smem_bytes(const DevScene &s) {
-    return (size_t)s.n_nodes * 32 + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 + (size_t)s.n_slots * 8;
+    return (size_t)s.n_nodes * 32 + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 +
+           (size_t)s.n_quad_slots * 16 * RT_QUAD_F4 + (size_t)s.n_slots * 8;
 }
 
 #define RT_LOCAL_STACK 64
 
 // Stage the scene arrays in shared memory (LDG.128 -> STS.128), return the carved pointers.
 struct SmemScene {
-    const F4 *nodes, *sph, *mats;
+    const F4 *nodes, *sph, *mats, *quads;
     const I2 *meta;
     uint32_t *stack;
 };
@@ -88,7 +90,8 @@ __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned ch
     F4 *nodes = reinterpret_cast<F4 *>(smem);
     F4 *sph = nodes + 2 * (size_t)sc.n_nodes;
     F4 *mats = sph + sc.n_slots;
-    I2 *meta = reinterpret_cast<I2 *>(mats + 2 * (size_t)sc.n_mats);
+    F4 *quads = mats + 2 * (size_t)sc.n_mats;
+    I2 *meta = reinterpret_cast<I2 *>(quads + (size_t)RT_QUAD_F4 * sc.n_quad_slots);
     uint32_t *stack = reinterpret_cast<uint32_t *>(meta + sc.n_slots + (sc.n_slots & 1));
     const uint4 *src;
     uint4 *dst;
@@ -98,12 +101,14 @@ __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned ch
     for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) dst[i] = __ldg(src + i);
     src = reinterpret_cast<const uint4 *>(sc.mats), dst = reinterpret_cast<uint4 *>(mats);
     for (uint32_t i = threadIdx.x; i < 2 * sc.n_mats; i += blockDim.x) dst[i] = __ldg(src + i);
+    src = reinterpret_cast<const uint4 *>(sc.quads), dst = reinterpret_cast<uint4 *>(quads);
+    for (uint32_t i = threadIdx.x; i < RT_QUAD_F4 * sc.n_quad_slots; i += blockDim.x) dst[i] = __ldg(src + i);
     const uint2 *s2 = reinterpret_cast<const uint2 *>(sc.meta);
     uint2 *d2 = reinterpret_cast<uint2 *>(meta);
     for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) d2[i] = __ldg(s2 + i);
     __syncthreads();
     SmemScene r;
-    r.nodes = nodes, r.sph = sph, r.mats = mats, r.meta = meta, r.stack = stack;
+    r.nodes = nodes, r.sph = sph, r.mats = mats, r.quads = quads, r.meta = meta, r.stack = stack;
     return r;
 }
 
@@ -132,15 +137,15 @@ struct RenderParams {
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
 
 // BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
-template <int BLOCK, int MINB, bool SMEM, bool COUNT>
+template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS>
 __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats;
+    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
     const I2 *meta = p.sc.meta;
     uint32_t *stack_mem = nullptr;
     if (SMEM) {
         SmemScene s = stage_scene(p.sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, mats = s.mats, meta = s.meta, stack_mem = s.stack;
+        nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta, stack_mem = s.stack;
     }
     typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
     Stack stack;
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 
         // ---- one path segment: ray.go:32-54 unrolled front to back ----
         HitRec h;
-        trace_closest<Stack, COUNT>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc);
+        trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads);
         n_rays++;
         bool done;
         if (h.slot == RT_REF_NONE) {
@@ -206,11 +211,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
             done = true;
         } else {
             n_hits++;
-            const F4 s = sph[h.slot];
-            const int mi = meta[h.slot].y;
-            const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
             V3 atten, emitted;
-            const bool scattered = shade_hit(m0, m1, p.sc.images, s, h.t, rng, o, d, atten, emitted);
+            bool scattered;
+            if (QUADS && (h.slot & RT_HIT_QUAD)) {
+                const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
+                const uint32_t mi = __float_as_uint(q[1].w);
+                const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
+                scattered = shade_hit_quad(m0, m1, p.sc.images, q, h.t, rng, o, d, atten, emitted);
+            } else {
+                const F4 s = sph[h.slot];
+                const int mi = meta[h.slot].y;
+                const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
+                scattered = shade_hit(m0, m1, p.sc.images, s, h.t, rng, o, d, atten, emitted);
+            }
             rad = rad + thr * emitted; // ray.go:41,50
             if (!scattered) {
                 done = true; // ray.go:44-46
@@ -497,18 +510,18 @@ __global__ void resolve_kernel(const float *__restrict__ accum, uint8_t *__restr
 // ---------------------------------------------------------------------------------------------
 // parity hooks
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK, bool SMEM>
+template <int BLOCK, bool SMEM, bool QUADS>
 __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ DevScene sc, const float *__restrict__ origins,
                                                       const float *__restrict__ dirs, long long n, float tmin, float tmax,
                                                       int32_t *__restrict__ id_out, float *__restrict__ t_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const F4 *nodes = sc.nodes, *sph = sc.sph;
+    const F4 *nodes = sc.nodes, *sph = sc.sph, *quads = sc.quads;
     const I2 *meta = sc.meta;
     typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
     Stack stack;
     if constexpr (SMEM) {
         SmemScene s = stage_scene(sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, meta = s.meta;
+        nodes = s.nodes, sph = s.sph, quads = s.quads, meta = s.meta;
         stack.base = s.stack + threadIdx.x;
         stack.stride = BLOCK;
     }
@@ -516,11 +529,11 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ De
         const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         HitRec h;
-        trace_closest<Stack, false>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr);
+        trace_closest<Stack, false, QUADS>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, quads);
         if (h.slot == RT_REF_NONE) {
             id_out[i] = -1, t_out[i] = 0.0f;
         } else {
-            id_out[i] = meta[h.slot].x, t_out[i] = h.t;
+            id_out[i] = slot_object_id(h.slot, meta, quads), t_out[i] = h.t;
         }
     }
 }
@@ -604,7 +617,7 @@ struct rt_scene {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    std::vector<rt_sphere> spheres;
+    ScenePrims prims;
     FlatBvh bvh;
     double center[3] = {0, 0, 0};
     double extent90 = 0;
@@ -616,7 +629,8 @@ struct rt_scene {
     bool use_pool = false; // pool-variant megakernel (RT_B200_KERNEL=pool)
     int pool_block = 512, pool_k = 4;
     // device buffers
-    F4 *d_nodes = nullptr, *d_sph = nullptr, *d_mats = nullptr;
+    F4 *d_nodes = nullptr, *d_sph = nullptr, *d_mats = nullptr, *d_quads = nullptr;
+    bool has_quads = false;
     I2 *d_meta = nullptr;
     DevImage *d_images = nullptr;
     std::vector<uint16_t *> d_texels;
@@ -672,7 +686,20 @@ static int validate_desc(const rt_scene_desc *d) {
     if ((d->n_spheres && !d->spheres) || (d->n_materials && !d->materials) || (d->n_textures && !d->textures) ||
         (d->n_images && !d->images))
         return fail(RT_ERR_INVALID_ARGUMENT, "null array with non-zero count");
-    if (d->n_spheres >= (1ull << 28)) return fail(RT_ERR_INVALID_ARGUMENT, "too many spheres (%llu)", (unsigned long long)d->n_spheres);
+    if (d->n_quads && !d->quads) return fail(RT_ERR_INVALID_ARGUMENT, "null array with non-zero count");
+    if (d->n_spheres >= (1ull << 27) || d->n_quads >= (1ull << 27))
+        return fail(RT_ERR_INVALID_ARGUMENT, "too many hittables (%llu spheres, %llu quads)", (unsigned long long)d->n_spheres,
+                    (unsigned long long)d->n_quads);
+    if ((d->sphere_ids != nullptr) != (d->quad_ids != nullptr) && d->n_spheres && d->n_quads)
+        return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids and quad_ids must be given together");
+    for (uint64_t i = 0; i < d->n_quads; i++) {
+        const rt_quad &q = d->quads[i];
+        if (q.material >= d->n_materials)
+            return fail(RT_ERR_INVALID_ARGUMENT, "quad %llu: material %u out of range", (unsigned long long)i, q.material);
+        for (int k = 0; k < 3; k++)
+            if (!std::isfinite(q.q[k]) || !std::isfinite(q.u[k]) || !std::isfinite(q.v[k]))
+                return fail(RT_ERR_INVALID_ARGUMENT, "quad %llu: non-finite geometry", (unsigned long long)i);
+    }
     for (uint64_t i = 0; i < d->n_spheres; i++) {
         const rt_sphere &s = d->spheres[i];
         if (s.material >= d->n_materials)
@@ -702,6 +729,7 @@ static void free_scene(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaFree(s->d_nodes), cudaFree(s->d_sph), cudaFree(s->d_mats), cudaFree(s->d_meta), cudaFree(s->d_images);
+    cudaFree(s->d_quads);
     for (auto p : s->d_texels) cudaFree(p);
     cudaFree(s->d_counter), cudaFree(s->d_stats);
     for (auto e : s->events) cudaEventDestroy(e);
@@ -724,15 +752,20 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     s->stream = s->own_stream;
 
-    s->spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
-    compute_scene_center(s->spheres.data(), s->spheres.size(), s->center, &s->extent90);
+    if (!load_scene_prims(desc, &s->prims))
+        return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
+    s->has_quads = !s->prims.quads.empty();
+    compute_scene_center(s->prims, s->center, &s->extent90);
     s->origin_radius = desc->ray_origin_radius > 0 ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
-    build_flat_bvh(s->spheres.data(), s->spheres.size(), s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh);
+    build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh);
 
     std::vector<F4> mats;
     pack_materials(desc, &mats);
 
-    const size_t n_nodes = s->bvh.nodes.size() / 2, n_slots = s->bvh.sph.size();
+    const size_t n_nodes = s->bvh.nodes.size() / 2, n_slots = s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
+    CU(cudaMalloc(&s->d_quads, std::max<size_t>(1, n_qslots) * 16 * RT_QUAD_F4));
+    if (n_qslots)
+        CU(cudaMemcpyAsync(s->d_quads, s->bvh.quad.data(), n_qslots * 16 * RT_QUAD_F4, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_nodes) * 32));
     CU(cudaMalloc(&s->d_sph, std::max<size_t>(1, n_slots) * 16));
     CU(cudaMalloc(&s->d_meta, std::max<size_t>(1, n_slots) * 8));
@@ -775,11 +808,12 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
 
     s->dev.nodes = s->d_nodes, s->dev.sph = s->d_sph, s->dev.meta = s->d_meta, s->dev.mats = s->d_mats;
     s->dev.images = s->d_images;
+    s->dev.quads = s->d_quads, s->dev.n_quad_slots = (uint32_t)n_qslots;
     s->dev.root_ref = s->bvh.root_ref;
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
     s->dev.stack_depth = s->bvh.max_depth + 2;
     s->block = env_int("RT_B200_BLOCK", 256);
-    if (s->block != 256 && s->block != 512 && s->block != 1024) s->block = 256;
+    if (s->block != 256 && s->block != 512) s->block = 256;
     s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 1);
     {
         const char *kv = getenv("RT_B200_KERNEL");
@@ -825,9 +859,9 @@ extern "C" int rt_scene_set_stream(rt_scene *scene, void *cuda_stream) {
 
 // Grow the BVH padding when ray origins lie outside the radius it was built for.
 static int ensure_origin_radius(rt_scene *s, double needed) {
-    if (needed <= s->origin_radius || s->spheres.empty()) return RT_OK;
+    if (needed <= s->origin_radius || s->prims.size() == 0) return RT_OK;
     s->origin_radius = (float)(needed * 1.25);
-    refit_flat_bvh(s->spheres.data(), s->spheres.size(), s->origin_radius, &s->bvh);
+    refit_flat_bvh(s->prims, s->origin_radius, &s->bvh);
     int rc = upload_nodes(s);
     if (rc != RT_OK) return rc;
     CU(cudaStreamSynchronize(s->stream));
@@ -842,9 +876,9 @@ static double dist_to_center(const rt_scene *s, const float *p) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK, int MINB, bool SMEM, bool COUNT>
+template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS>
 static int launch_render_t(rt_scene *s, const RenderParams &p) {
-    auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT>;
+    auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT, QUADS>;
     if (s->grid_cache[COUNT] == 0) { // once per handle: opt in to the dynamic shared memory, size the grid
         const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -859,18 +893,15 @@ static int launch_render_t(rt_scene *s, const RenderParams &p) {
     return RT_OK;
 }
 
-// (block, min blocks/SM) instances: 256x3 = 24 warps at <= 85 registers, 256x4 / 512x2 / 1024x1 =
+// (block, min blocks/SM) instances: 256x3 = 24 warps at <= 85 registers (default), 256x4 / 512x2 =
 // 32 warps at <= 64 registers.  RT_B200_BLOCK / RT_B200_MINB pick one (tuning knob).
-template <bool SMEM, bool COUNT>
+template <bool SMEM, bool COUNT, bool QUADS>
 static int launch_render_b(rt_scene *s, const RenderParams &p) {
     const int key = s->block * 10 + s->minb;
     switch (key) {
-    case 2562: return launch_render_t<256, 2, SMEM, COUNT>(s, p);
-    case 2564: return launch_render_t<256, 4, SMEM, COUNT>(s, p);
-    case 5121: return launch_render_t<512, 1, SMEM, COUNT>(s, p);
-    case 5122: return launch_render_t<512, 2, SMEM, COUNT>(s, p);
-    case 10241: return launch_render_t<1024, 1, SMEM, COUNT>(s, p);
-    default: return launch_render_t<256, 3, SMEM, COUNT>(s, p);
+    case 2564: return launch_render_t<256, 4, SMEM, COUNT, QUADS>(s, p);
+    case 5122: return launch_render_t<512, 2, SMEM, COUNT, QUADS>(s, p);
+    default: return launch_render_t<256, 3, SMEM, COUNT, QUADS>(s, p);
     }
 }
 
@@ -894,25 +925,20 @@ static int launch_pool_t(rt_scene *s, const RenderParams &p) {
 
 template <bool SMEM, bool COUNT>
 static int launch_pool_b(rt_scene *s, const RenderParams &p) {
-    const int key = s->pool_block * 10 + s->pool_k;
-    switch (key) {
-    case 5122: return launch_pool_t<512, 2, SMEM, COUNT>(s, p);
-    case 5128: return launch_pool_t<512, 8, SMEM, COUNT>(s, p);
-    case 7682: return launch_pool_t<768, 2, SMEM, COUNT>(s, p);
-    case 7683: return launch_pool_t<768, 3, SMEM, COUNT>(s, p);
-    case 10242: return launch_pool_t<1024, 2, SMEM, COUNT>(s, p);
-    case 2564: return launch_pool_t<256, 4, SMEM, COUNT>(s, p);
-    default: return launch_pool_t<512, 4, SMEM, COUNT>(s, p);
-    }
+    if (s->pool_block == 768 && s->pool_k == 2) return launch_pool_t<768, 2, SMEM, COUNT>(s, p);
+    return launch_pool_t<512, 4, SMEM, COUNT>(s, p);
+}
+
+template <bool SMEM, bool COUNT>
+static int launch_render_q(rt_scene *s, const RenderParams &p) {
+    if (s->has_quads) return launch_render_b<SMEM, COUNT, true>(s, p);
+    if (s->use_pool) return launch_pool_b<SMEM, COUNT>(s, p); // experimental pool variant: spheres only
+    return launch_render_b<SMEM, COUNT, false>(s, p);
 }
 
 static int launch_render(rt_scene *s, const RenderParams &p, bool count) {
-    if (s->use_pool) {
-        if (s->use_smem) return count ? launch_pool_b<true, true>(s, p) : launch_pool_b<true, false>(s, p);
-        return count ? launch_pool_b<false, true>(s, p) : launch_pool_b<false, false>(s, p);
-    }
-    if (s->use_smem) return count ? launch_render_b<true, true>(s, p) : launch_render_b<true, false>(s, p);
-    return count ? launch_render_b<false, true>(s, p) : launch_render_b<false, false>(s, p);
+    if (s->use_smem) return count ? launch_render_q<true, true>(s, p) : launch_render_q<true, false>(s, p);
+    return count ? launch_render_q<false, true>(s, p) : launch_render_q<false, false>(s, p);
 }
 
 static int check_camera(const rt_camera *c) {
@@ -1095,17 +1121,17 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
     return RT_OK;
 }
 
-template <int BLOCK>
+template <int BLOCK, bool QUADS>
 static int launch_trace_t(rt_scene *s, const float *d_o, const float *d_d, int64_t n, float tmin, float tmax,
                           int32_t *d_id, float *d_t) {
     const int grid = (int)std::min<int64_t>((n + BLOCK - 1) / BLOCK, (int64_t)s->sm_count * 16);
-    if (s->use_smem) {
-        auto kern = trace_kernel<BLOCK, true>;
-        const size_t smem = smem_total_bytes(s->dev, BLOCK);
+    const size_t smem = smem_total_bytes(s->dev, BLOCK);
+    if (s->use_smem && smem <= s->smem_optin) {
+        auto kern = trace_kernel<BLOCK, true, QUADS>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<std::min(grid, s->sm_count * 2), BLOCK, smem, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);
     } else {
-        trace_kernel<BLOCK, false><<<grid, BLOCK, 0, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);
+        trace_kernel<BLOCK, false, QUADS><<<grid, BLOCK, 0, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);
     }
     CU(cudaGetLastError());
     return RT_OK;
@@ -1134,8 +1160,8 @@ extern "C" int rt_trace(rt_scene *scene, const float *origins, const float *dirs
         cleanup();
         return fail(e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA, "rt_trace setup: %s", cudaGetErrorString(e));
     }
-    rc = scene->block == 256 ? launch_trace_t<256>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t)
-                             : launch_trace_t<512>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t);
+    rc = scene->has_quads ? launch_trace_t<256, true>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t)
+                          : launch_trace_t<256, false>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t);
     if (rc == RT_OK) {
         e = cudaMemcpyAsync(id_out, d_id, (size_t)n * 4, cudaMemcpyDeviceToHost, scene->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(t_out, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, scene->stream);

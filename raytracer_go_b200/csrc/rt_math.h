@@ -34,6 +34,8 @@ RT_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }     
 // vec3.go:115-117 and 137-139: (x*x + y*y) + z*z, left to right, unfused
 RT_HD float lensq(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 RT_HD float dot(V3 l, V3 r) { return l.x * r.x + l.y * r.y + l.z * r.z; }
+// vec3.go:129-135
+RT_HD V3 cross(V3 l, V3 r) { return v3(l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x); }
 // float32(math.Sqrt(float64(x))) == correctly rounded sqrtf(x) (vec3.go:105, hittables.go:108)
 RT_HD float sqrt32(float x) {
 #if defined(__CUDA_ARCH__)

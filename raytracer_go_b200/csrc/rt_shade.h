@@ -81,6 +81,8 @@ RT_HD void generate_ray(const DevCamera &c, PathRng &rng, int i, int j, V3 &orig
 struct HitInfo {
     V3 point, normal;
     bool front;
+    bool is_quad;  // u, v below are valid (a quad's alpha, beta); a sphere's UV is computed on demand
+    float u, v;
 };
 
 // hittables.go:118-120 and NewHitInfo (hittables.go:22-37)
@@ -90,6 +92,21 @@ RT_HD void complete_hit(const F4 &s, V3 o, V3 d, float t, HitInfo &hi) {
     bool front = dot(d, norm) < 0;
     if (!front) norm = norm * -1.0f;
     hi.point = point, hi.normal = norm, hi.front = front;
+    hi.is_quad = false, hi.u = 0, hi.v = 0;
+}
+
+// Quad.Hit's HitInfo (hittables.go:180-190): point, alpha/beta as (u, v), the quad's normal flipped
+// against the ray.  `q` is the 5 x F4 device record (rt_trace.h).
+RT_HD void complete_hit_quad(const F4 *__restrict__ q, V3 o, V3 d, float t, HitInfo &hi) {
+    const V3 p = d * t + o;
+    const V3 ph = p - v3(q[0].x, q[0].y, q[0].z);
+    const V3 w = v3(q[3].x, q[3].y, q[3].z);
+    hi.u = dot(w, cross(ph, v3(q[2].x, q[2].y, q[2].z)));
+    hi.v = dot(w, cross(v3(q[1].x, q[1].y, q[1].z), ph));
+    V3 norm = v3(q[4].x, q[4].y, q[4].z);
+    const bool front = dot(d, norm) < 0;
+    if (!front) norm = norm * -1.0f;
+    hi.point = p, hi.normal = norm, hi.front = front, hi.is_quad = true;
 }
 
 // hittables.go:122-126.  `outward` is the normal BEFORE the front-face flip.
@@ -122,8 +139,8 @@ RT_HD V3 image_texture(const DevImage &im, V3 oob, float u, float v) {
 }
 
 // Texture.GetTexture for the texture folded into material record (m0, m1).
-RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, const DevImage *images, V3 point,
-                       V3 outward) {
+RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, const DevImage *images, const HitInfo &hi) {
+    const V3 point = hi.point;
     const uint32_t tex = RT_CODE_TEX(code);
     if (tex == RT_TEX_CHECKER) { // materials.go:127-137
         const float inv = m0.w;
@@ -134,8 +151,8 @@ RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, const DevImage
         return v3(m1.x, m1.y, m1.z);
     }
     if (tex == RT_TEX_IMAGE) {
-        float u, v;
-        sphere_uv(outward, u, v);
+        float u = hi.u, v = hi.v;
+        if (!hi.is_quad) sphere_uv(hi.front ? hi.normal : hi.normal * -1.0f, u, v); // the outward normal
         return image_texture(images[RT_CODE_IMG(code)], v3(m0.x, m0.y, m0.z), u, v);
     }
     return v3(m0.x, m0.y, m0.z); // materials.go:155-157
@@ -155,10 +172,8 @@ RT_HD float reflectance(float cos_theta, float eta) {
 // is always written.  On scatter, (o, d) become the scattered ray and `atten` its attenuation.
 // The work shared by several materials (the unit-sphere sample of Lambertian and Metal, Unit(dir)
 // of Metal and Dielectric) is hoisted so that lanes with different materials run it together.
-RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F4 &sphere, float t,
-                     PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
-    HitInfo hi;
-    complete_hit(sphere, o, d, t, hi);
+RT_HD bool shade_surface(const F4 &m0, const F4 &m1, const DevImage *images, const HitInfo &hi,
+                         PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
     const uint32_t code = as_uint(m1.w);
     const uint32_t kind = RT_CODE_MAT(code);
     emitted = v3(0, 0, 0);
@@ -168,8 +183,7 @@ RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F
     if (kind == RT_MAT_LAMBERTIAN) { // materials.go:33-42
         V3 dir = hi.normal + ru;
         if (near_zero(dir)) dir = hi.normal;
-        const V3 outward = hi.front ? hi.normal : hi.normal * -1.0f;
-        atten = texture_value(m0, m1, code, images, hi.point, outward);
+        atten = texture_value(m0, m1, code, images, hi);
         o = hi.point, d = dir;
         return true;
     }
@@ -200,9 +214,24 @@ RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F
         return true;
     }
     // DiffuseLight: emits its texture, never scatters (materials.go:301-313)
-    const V3 outward = hi.front ? hi.normal : hi.normal * -1.0f;
-    emitted = texture_value(m0, m1, code, images, hi.point, outward);
+    emitted = texture_value(m0, m1, code, images, hi);
     return false;
+}
+
+// Sphere hit (hittables.go:118-128) then Emit + Scatter.
+RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F4 &sphere, float t,
+                     PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
+    HitInfo hi;
+    complete_hit(sphere, o, d, t, hi);
+    return shade_surface(m0, m1, images, hi, rng, o, d, atten, emitted);
+}
+
+// Quad hit (hittables.go:180-190) then Emit + Scatter.
+RT_HD bool shade_hit_quad(const F4 &m0, const F4 &m1, const DevImage *images, const F4 *__restrict__ quad, float t,
+                          PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
+    HitInfo hi;
+    complete_hit_quad(quad, o, d, t, hi);
+    return shade_surface(m0, m1, images, hi, rng, o, d, atten, emitted);
 }
 
 // camera.go:261 (sum * (1/spp)), vec3.go:162-166 (sqrt), 145-152 (clamp, *255.999), 141-143 (int())

@@ -13,8 +13,11 @@
 // Device layout (uploaded once, depth-first order, siblings adjacent):
 //   node i  = 2 x F4 = 32 bytes: (min.x, min.y, min.z, ref) (max.x, max.y, max.z, unused)
 //   ref     = inner: index of the first of its two children (children are nodes ref, ref+1)
-//             leaf : RT_LEAF | first_slot << 3 | (count-1)        (1..8 spheres)
-//   slot s  = F4 (cx, cy, cz, r) + I2 (object index, material index)
+//             leaf : RT_LEAF | first_slot << 3 | (count-1)        (1..8 spheres), or
+//                    RT_LEAF | RT_LEAF_QUAD | first_slot << 3 | (count-1)   (quads, own slot array)
+//   sphere slot s = F4 (cx, cy, cz, r) + I2 (object ID, material index)
+//   quad slot s   = 5 x F4: (Q.xyz, D) (u.xyz, bits material) (v.xyz, bits object ID) (w.xyz, 0)
+//                   (normal.xyz, 0) — Q, u, v and the fields NewQuad derives (hittables.go:149-165)
 #ifndef RT_TRACE_H
 #define RT_TRACE_H
 
@@ -34,12 +37,16 @@ struct RT_ALIGN(8) I2 {
 };
 
 #define RT_LEAF 0x80000000u
-#define RT_REF_NONE 0xFFFFFFFFu /* empty scene / stack bottom */
+#define RT_LEAF_QUAD 0x40000000u      /* with RT_LEAF: the leaf holds quads */
+#define RT_LEAF_SLOT_MASK 0x3FFFFFFFu /* clears the two flag bits */
+#define RT_REF_NONE 0xFFFFFFFFu       /* empty scene / stack bottom */
 #define RT_MAX_LEAF 8
+#define RT_QUAD_F4 5                  /* F4 per quad slot */
+#define RT_HIT_QUAD 0x40000000u       /* HitRec.slot flag: the slot indexes the quad array */
 
 struct HitRec {
     float t;
-    uint32_t slot; // RT_REF_NONE on miss
+    uint32_t slot; // RT_REF_NONE on miss; RT_HIT_QUAD | quad slot for a quad
 };
 
 struct WorkCounters {
@@ -139,10 +146,35 @@ RT_HD bool sphere_candidate(const F4 &s, V3 o, V3 d, float a, float tmin, float 
     return true;
 }
 
-template <class Stack, bool COUNT>
+// hittables.go:167-190 for one quad, in the reference's operation order.  A root beyond tbest is
+// dropped before the in-plane test (the reference tests the interval first too, :176).
+RT_HD bool quad_candidate(const F4 *__restrict__ q, V3 o, V3 d, float tmin, float tbest, float &t_out) {
+    const V3 n = v3(q[4].x, q[4].y, q[4].z);
+    const float denom = dot(d, n);                            // :168
+    if (fabs((double)denom) < 1e-8) return false;             // :170
+    const float t = div32(q[0].w - dot(n, o), denom);         // :174
+    if (!(tmin < t) || !(t <= tbest)) return false;           // :176 (ties are resolved by the caller)
+    const V3 p = d * t + o;                                   // :180
+    const V3 ph = p - v3(q[0].x, q[0].y, q[0].z);             // :181
+    const V3 w = v3(q[3].x, q[3].y, q[3].z);
+    const float alpha = dot(w, cross(ph, v3(q[2].x, q[2].y, q[2].z))); // :182
+    const float beta = dot(w, cross(v3(q[1].x, q[1].y, q[1].z), ph));  // :183
+    if (alpha < 0 || 1 < alpha || beta < 0 || 1 < beta) return false;  // :185, 192-194
+    t_out = t;
+    return true;
+}
+
+// Object ID of a hit slot (only needed to break exact ties).
+RT_HD int32_t slot_object_id(uint32_t slot, const I2 *__restrict__ meta, const F4 *__restrict__ quads) {
+    if (slot & RT_HIT_QUAD) return (int32_t)as_uint(quads[(size_t)RT_QUAD_F4 * (slot & ~RT_HIT_QUAD) + 2].w);
+    return meta[slot].x;
+}
+
+template <class Stack, bool COUNT, bool QUADS = false>
 RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sph,
                          const I2 *__restrict__ meta, uint32_t root_ref, V3 o, V3 d, float tmin,
-                         float tmax, Stack &stack, HitRec &hit, WorkCounters *wc) {
+                         float tmax, Stack &stack, HitRec &hit, WorkCounters *wc,
+                         const F4 *__restrict__ quads = nullptr) {
     const V3 inv = v3(cull_rcp(d.x), cull_rcp(d.y), cull_rcp(d.z));
     const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
     const float a = lensq(d);
@@ -176,19 +208,35 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
             }
         }
         if (ref == RT_REF_NONE) break;
-        const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
-        for (uint32_t s = first; s < first + count; s++) {
-            const F4 sp = sph[s];
-            float t;
-            if (COUNT) wc->sphere_tests += 1;
-            if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
-            if (t < tbest) {
-                tbest = t, best_slot = s, have_id = false;
-            } else if (t == tbest && best_slot != RT_REF_NONE) {
-                // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
-                if (!have_id) best_id = meta[best_slot].x, have_id = true;
-                const int32_t id = meta[s].x;
-                if (id < best_id) best_slot = s, best_id = id;
+        const uint32_t first = (ref & RT_LEAF_SLOT_MASK) >> 3, count = (ref & 7u) + 1;
+        if (QUADS && (ref & RT_LEAF_QUAD)) {
+            for (uint32_t s = first; s < first + count; s++) {
+                float t;
+                if (COUNT) wc->sphere_tests += 1;
+                if (!quad_candidate(quads + (size_t)RT_QUAD_F4 * s, o, d, tmin, tbest, t)) continue;
+                const uint32_t hs = s | RT_HIT_QUAD;
+                if (t < tbest) {
+                    tbest = t, best_slot = hs, have_id = false;
+                } else if (t == tbest && best_slot != RT_REF_NONE) {
+                    if (!have_id) best_id = slot_object_id(best_slot, meta, quads), have_id = true;
+                    const int32_t id = slot_object_id(hs, meta, quads);
+                    if (id < best_id) best_slot = hs, best_id = id;
+                }
+            }
+        } else {
+            for (uint32_t s = first; s < first + count; s++) {
+                const F4 sp = sph[s];
+                float t;
+                if (COUNT) wc->sphere_tests += 1;
+                if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
+                if (t < tbest) {
+                    tbest = t, best_slot = s, have_id = false;
+                } else if (t == tbest && best_slot != RT_REF_NONE) {
+                    // exact tie: World.Hit keeps the earlier object (strict `<`, hittables.go:59-69)
+                    if (!have_id) best_id = QUADS ? slot_object_id(best_slot, meta, quads) : meta[best_slot].x, have_id = true;
+                    const int32_t id = meta[s].x;
+                    if (id < best_id) best_slot = s, best_id = id;
+                }
             }
         }
         ref = stack.pop();

@@ -12,8 +12,8 @@
 //
 // What it does, in order:
 //  1. walks the world (a *BVH built by NewBVH, bvh.go:142, or a *World, hittables.go:39) by type
-//     switch and fills pointer-free C arrays: spheres, materials, textures, images — materials and
-//     textures de-duplicated by pointer identity;
+//     switch and fills pointer-free C arrays: spheres, quads (Quad and Box, hittables.go:138-216),
+//     materials, textures, images — materials and textures de-duplicated by pointer identity;
 //  2. copies the derived camera fields computed by Camera.init (camera.go:128-166) into rt_camera;
 //  3. makes ONE call, rt_render, which returns width*height RGB8 triplets (GetPixelColor + gamma +
 //     quantise, camera.go:254-263, 212-214, on the GPU);
@@ -46,13 +46,19 @@ type B200Options struct {
 
 type b200Flat struct {
 	spheres   []C.rt_sphere
+	quads     []C.rt_quad
+	sphereIDs []C.uint32_t // object ID = first-seen position in the walk (World.hittables order)
+	quadIDs   []C.uint32_t
 	materials []C.rt_material
 	textures  []C.rt_texture
 	images    []image.Image
 	matIndex  map[Material]uint32
 	texIndex  map[Texture]uint32
 	seen      map[Hittable]bool
+	seenQuads map[quadKey]bool
 }
+
+type quadKey struct{ Q, u, v Vec3 }
 
 func (f *b200Flat) texture(t Texture) (uint32, error) {
 	if i, ok := f.texIndex[t]; ok {
@@ -156,9 +162,26 @@ func (f *b200Flat) walk(h Hittable) error {
 		if err != nil {
 			return err
 		}
+		f.sphereIDs = append(f.sphereIDs, C.uint32_t(len(f.spheres)+len(f.quads)))
 		f.spheres = append(f.spheres, C.rt_sphere{
 			cx: C.float(hh.Center.X), cy: C.float(hh.Center.Y), cz: C.float(hh.Center.Z),
 			r: C.float(hh.Radius), material: C.uint32_t(m)})
+		return nil
+	case Quad: // hittables.go:138-147 (stored by value: NewQuad returns Quad, main.go:152)
+		// a value type cannot be de-duplicated by pointer; a Quad reaches the walk once unless it is
+		// the only element of a one-element BVH node (bvh.go:162-165), where left == right
+		k := quadKey{hh.Q, hh.u, hh.v}
+		if f.seenQuads[k] {
+			return nil
+		}
+		f.seenQuads[k] = true
+		m, err := f.material(hh.material)
+		if err != nil {
+			return err
+		}
+		v3 := func(v Vec3) [3]C.float { return [3]C.float{C.float(v.X), C.float(v.Y), C.float(v.Z)} }
+		f.quadIDs = append(f.quadIDs, C.uint32_t(len(f.spheres)+len(f.quads)))
+		f.quads = append(f.quads, C.rt_quad{q: v3(hh.Q), u: v3(hh.u), v: v3(hh.v), material: C.uint32_t(m)})
 		return nil
 	default:
 		return fmt.Errorf("b200: hittable %T is outside the accelerated path", h)
@@ -187,7 +210,8 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 	if len(opt) > 0 {
 		o = opt[0]
 	}
-	f := &b200Flat{matIndex: map[Material]uint32{}, texIndex: map[Texture]uint32{}, seen: map[Hittable]bool{}}
+	f := &b200Flat{matIndex: map[Material]uint32{}, texIndex: map[Texture]uint32{}, seen: map[Hittable]bool{},
+		seenQuads: map[quadKey]bool{}}
 	if err := f.walk(world); err != nil {
 		return err
 	}
@@ -223,6 +247,12 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 	frees = append(frees, fr)
 	pi, fr := cArray(cimgs)
 	frees = append(frees, fr)
+	pq, fr := cArray(f.quads)
+	frees = append(frees, fr)
+	psi, fr := cArray(f.sphereIDs)
+	frees = append(frees, fr)
+	pqi, fr := cArray(f.quadIDs)
+	frees = append(frees, fr)
 
 	desc := C.rt_scene_desc{
 		abi_version: C.RT_B200_ABI_VERSION,
@@ -230,6 +260,8 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 		materials: (*C.rt_material)(pm), n_materials: C.uint32_t(len(f.materials)),
 		textures: (*C.rt_texture)(pt), n_textures: C.uint32_t(len(f.textures)),
 		images: (*C.rt_image)(pi), n_images: C.uint32_t(len(cimgs)),
+		quads: (*C.rt_quad)(pq), n_quads: C.uint64_t(len(f.quads)),
+		sphere_ids: (*C.uint32_t)(psi), quad_ids: (*C.uint32_t)(pqi),
 	}
 	var scene *C.rt_scene
 	if rc := C.rt_scene_create(&desc, C.int(o.Device), &scene); rc != C.RT_OK {

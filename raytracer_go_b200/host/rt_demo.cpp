@@ -1,6 +1,8 @@
-// rt_demo.cpp — main.go's randSpheres scene (main.go:227-289) written against the C++ mirror of the
-// reference API and rendered through librt_b200.so; writes a P3 PPM like the reference's out/img.ppm.
-//   rt_demo [width=400] [spp=500] [out=out/img.ppm] [scene_seed=0x5EED0001]
+// rt_demo.cpp — main.go's randSpheres (main.go:227-289) and cornellBox (main.go:194-225) scenes written
+// against the C++ mirror of the reference API and rendered through librt_b200.so; writes a P3 PPM like
+// the reference's out/img.ppm.
+//   rt_demo [width=400] [spp=500] [out=out/img.ppm] [scene_seed=0x5EED0001]      random spheres
+//   rt_demo cornell [width=600] [spp=200] [out=out/img.ppm]                       Cornell box
 // The reference seeds its scene RNG from the clock (main.go:246); here a fixed-seed SplitMix64
 // supplies rand.Float32() so runs are reproducible.
 #include <chrono>
@@ -23,7 +25,39 @@ struct Rand {
     }
 };
 
+static int cornell(int argc, char **argv) { // main.go:194-225
+    const int width = argc > 2 ? atoi(argv[2]) : 600;
+    const int spp = argc > 3 ? atoi(argv[3]) : 200;
+    const char *out = argc > 4 ? argv[4] : "out/img.ppm";
+    auto camera = NewCamera(1, width,
+                            {WithSamplesPerPixel(spp), WithMaxRayDepth(50), WithLookFrom(NewVec3(278, 278, -800)),
+                             WithLookAt(NewVec3(278, 278, 0)), WithFOVDegrees(40), WithDefocusAngleDegrees(0),
+                             WithBackgroundColor(NewVec3Zero())});
+    auto world = NewWorld();
+    auto red = NewLambertian(NewSolidColor(.65f, .05f, .05f));
+    auto white = NewLambertian(NewSolidColor(.73f, .73f, .73f));
+    auto green = NewLambertian(NewSolidColor(.12f, .45f, .15f));
+    auto light = NewDiffuseLight(NewSolidColor(15, 15, 15));
+    world->Add(NewQuad(NewVec3(555, 0, 0), NewVec3(0, 555, 0), NewVec3(0, 0, 555), green));
+    world->Add(NewQuad(NewVec3(0, 0, 0), NewVec3(0, 555, 0), NewVec3(0, 0, 555), red));
+    world->Add(NewQuad(NewVec3(343, 554, 332), NewVec3(-130, 0, 0), NewVec3(0, 0, -105), light));
+    world->Add(NewQuad(NewVec3(0, 0, 0), NewVec3(555, 0, 0), NewVec3(0, 0, 555), white));
+    world->Add(NewQuad(NewVec3(555, 555, 555), NewVec3(-555, 0, 0), NewVec3(0, 0, -555), white));
+    world->Add(NewQuad(NewVec3(0, 0, 555), NewVec3(555, 0, 0), NewVec3(0, 555, 0), white));
+    world->Add(Box(NewVec3(130, 0, 65), NewVec3(295, 165, 230), white));
+    world->Add(Box(NewVec3(265, 0, 295), NewVec3(430, 330, 460), white));
+    std::ofstream f(out);
+    if (!f) return fprintf(stderr, "cannot open %s\n", out), 2;
+    std::string err = camera->Render(NewBVHFromWorld(world), f);
+    if (!err.empty()) return fprintf(stderr, "render failed: %s\n", err.c_str()), 1;
+    const rt_stats &st = camera->last_stats;
+    printf("Finished: cornell box %dx%d, %d spp: %.1f Msamples/s device, %.1f Mrays/s\n", camera->c.width,
+           camera->c.height, spp, st.samples / (st.ms_render * 1e3), st.rays / (st.ms_render * 1e3));
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "cornell") return cornell(argc, argv);
     const int width = argc > 1 ? atoi(argv[1]) : 400;
     const int spp = argc > 2 ? atoi(argv[2]) : 500;
     const char *out = argc > 3 ? argv[3] : "out/img.ppm";

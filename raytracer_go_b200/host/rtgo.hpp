@@ -105,19 +105,36 @@ inline MaterialPtr NewDiffuseLight(TexturePtr emit) {
     return m;
 }
 
-// ---- hittables (hittables.go:39-94, bvh.go:132-140) ----
-struct Sphere {
-    Vec3 Center;
+// ---- hittables (hittables.go:39-94, 138-216, bvh.go:132-140) ----
+struct HittableObj {
+    enum Kind { SPHERE, QUAD } kind;
+    Vec3 a, b, c; // sphere: a = Center; quad: a = Q, b = u, c = v
     float Radius;
     MaterialPtr Mat;
 };
-using Hittable = std::shared_ptr<Sphere>; // the accelerated path covers spheres (quads next)
-inline Hittable NewSphere(Vec3 center, float radius, MaterialPtr mat) {
-    return std::make_shared<Sphere>(Sphere{center, radius, std::move(mat)});
+using Hittable = std::shared_ptr<HittableObj>;
+inline Hittable NewSphere(Vec3 center, float radius, MaterialPtr mat) { // hittables.go:85-94
+    return std::make_shared<HittableObj>(HittableObj{HittableObj::SPHERE, center, Vec3{}, Vec3{}, radius, std::move(mat)});
+}
+inline Hittable NewQuad(Vec3 Q, Vec3 u, Vec3 v, MaterialPtr mat) { // hittables.go:149-165 (derived fields: library)
+    return std::make_shared<HittableObj>(HittableObj{HittableObj::QUAD, Q, u, v, 0, std::move(mat)});
+}
+// hittables.go:200-216: the six quads of an axis-aligned box, in the reference's order
+inline std::vector<Hittable> Box(Vec3 a, Vec3 b, const MaterialPtr &mat) {
+    Vec3 mn{std::fmin(a.X, b.X), std::fmin(a.Y, b.Y), std::fmin(a.Z, b.Z)};
+    Vec3 mx{std::fmax(a.X, b.X), std::fmax(a.Y, b.Y), std::fmax(a.Z, b.Z)};
+    Vec3 dx{mx.X - mn.X, 0, 0}, dy{0, mx.Y - mn.Y, 0}, dz{0, 0, mx.Z - mn.Z};
+    auto neg = [](Vec3 v) { return Vec3{v.X * -1, v.Y * -1, v.Z * -1}; };
+    return {NewQuad(NewVec3(mn.X, mn.Y, mx.Z), dx, dy, mat),      NewQuad(NewVec3(mx.X, mn.Y, mx.Z), neg(dz), dy, mat),
+            NewQuad(NewVec3(mx.X, mn.Y, mn.Z), neg(dx), dy, mat), NewQuad(NewVec3(mn.X, mn.Y, mn.Z), dz, dy, mat),
+            NewQuad(NewVec3(mn.X, mx.Y, mx.Z), dx, neg(dz), mat), NewQuad(NewVec3(mn.X, mn.Y, mn.Z), dx, dz, mat)};
 }
 struct World {
     std::vector<Hittable> hittables;
     void Add(Hittable h) { hittables.push_back(std::move(h)); } // hittables.go:48-53: insertion order = object ID
+    void Add(const std::vector<Hittable> &hs) {
+        for (const auto &h : hs) hittables.push_back(h);
+    }
 };
 inline std::shared_ptr<World> NewWorld() { return std::make_shared<World>(); }
 // NewBVHFromWorld (bvh.go:138): the reference builds its random-axis pointer tree here; the device
@@ -154,6 +171,8 @@ struct Camera {
     std::string Render(const std::shared_ptr<BVH> &world, std::ostream &writer) {
         // flatten: materials / textures de-duplicated by pointer, spheres in insertion order
         std::vector<rt_sphere> spheres;
+        std::vector<rt_quad> quads;
+        std::vector<uint32_t> sphere_ids, quad_ids;
         std::vector<rt_material> materials;
         std::vector<rt_texture> textures;
         std::vector<rt_image> images;
@@ -204,7 +223,14 @@ struct Camera {
                 materials.push_back(r);
                 mi = mat_index[m] = (uint32_t)materials.size() - 1;
             }
-            spheres.push_back(rt_sphere{h->Center.X, h->Center.Y, h->Center.Z, h->Radius, mi});
+            const uint32_t object_id = (uint32_t)(spheres.size() + quads.size());
+            if (h->kind == HittableObj::SPHERE) {
+                spheres.push_back(rt_sphere{h->a.X, h->a.Y, h->a.Z, h->Radius, mi});
+                sphere_ids.push_back(object_id);
+            } else {
+                quads.push_back(rt_quad{{h->a.X, h->a.Y, h->a.Z}, {h->b.X, h->b.Y, h->b.Z}, {h->c.X, h->c.Y, h->c.Z}, mi});
+                quad_ids.push_back(object_id);
+            }
         }
         rt_scene_desc desc{};
         desc.abi_version = RT_B200_ABI_VERSION;
@@ -212,6 +238,8 @@ struct Camera {
         desc.materials = materials.data(), desc.n_materials = (uint32_t)materials.size();
         desc.textures = textures.data(), desc.n_textures = (uint32_t)textures.size();
         desc.images = images.data(), desc.n_images = (uint32_t)images.size();
+        desc.quads = quads.data(), desc.n_quads = quads.size();
+        desc.sphere_ids = sphere_ids.data(), desc.quad_ids = quad_ids.data();
         rt_scene *scene = nullptr;
         if (rt_scene_create(&desc, device, &scene) != RT_OK) return rt_last_error();
         const int w = c.width, h = c.height;

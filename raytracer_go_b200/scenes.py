@@ -21,11 +21,13 @@ F = np.float32
 SPHERE_DT = np.dtype([("cx", F), ("cy", F), ("cz", F), ("r", F), ("material", np.uint32)])
 MATERIAL_DT = np.dtype([("kind", np.uint32), ("albedo", F, 3), ("fuzz", F), ("ior", F),
                         ("texture", np.uint32)])
+QUAD_DT = np.dtype([("q", F, 3), ("u", F, 3), ("v", F, 3), ("material", np.uint32)])
 TEXTURE_DT = np.dtype([("kind", np.uint32), ("a", F, 3), ("b", F, 3), ("scale", F),
                        ("image", np.uint32), ("oob", F, 3)])
 assert SPHERE_DT.itemsize == C.sizeof(abi.rt_sphere)
 assert MATERIAL_DT.itemsize == C.sizeof(abi.rt_material)
 assert TEXTURE_DT.itemsize == C.sizeof(abi.rt_texture)
+assert QUAD_DT.itemsize == C.sizeof(abi.rt_quad)
 
 SCENE_SEED_RANDOM = 0x5EED0001
 TEXTURE_SEED_EARTH = 0x5EED0003
@@ -36,8 +38,13 @@ RENDER_SEED = 0xC0FFEE
 class SceneData:
     """Flat, pointer-free scene (what the Go bridge would fill by walking World.hittables)."""
 
-    def __init__(self, spheres, materials, textures, images=(), ray_origin_radius=0.0, name=""):
+    def __init__(self, spheres, materials, textures, images=(), ray_origin_radius=0.0, name="", quads=None,
+                 sphere_ids=None, quad_ids=None):
         self.spheres = np.ascontiguousarray(spheres, dtype=SPHERE_DT)
+        self.quads = np.ascontiguousarray(quads if quads is not None else np.zeros(0, QUAD_DT), dtype=QUAD_DT)
+        # object IDs = position in World.hittables (hittables.go:48-53); None = spheres first, then quads
+        self.sphere_ids = None if sphere_ids is None else np.ascontiguousarray(sphere_ids, np.uint32)
+        self.quad_ids = None if quad_ids is None else np.ascontiguousarray(quad_ids, np.uint32)
         self.materials = np.ascontiguousarray(materials, dtype=MATERIAL_DT)
         self.textures = np.ascontiguousarray(textures, dtype=TEXTURE_DT)
         self.images = [np.ascontiguousarray(im, dtype=np.uint16) for im in images]  # (h, w, 3)
@@ -61,15 +68,26 @@ class SceneData:
         d.images = imgs
         d.n_images = len(self.images)
         d.ray_origin_radius = self.ray_origin_radius
+        d.quads = self.quads.ctypes.data_as(C.POINTER(abi.rt_quad))
+        d.n_quads = len(self.quads)
+        if self.sphere_ids is not None or self.quad_ids is not None:
+            sid = self.sphere_ids if self.sphere_ids is not None else np.zeros(0, np.uint32)
+            qid = self.quad_ids if self.quad_ids is not None else np.zeros(0, np.uint32)
+            d.sphere_ids = sid.ctypes.data_as(C.POINTER(C.c_uint32))
+            d.quad_ids = qid.ctypes.data_as(C.POINTER(C.c_uint32))
+            return d, (imgs, self, sid, qid)
         return d, (imgs, self)
 
+    def n_objects(self):
+        return len(self.spheres) + len(self.quads)
+
     def nbytes(self):
-        return (self.spheres.nbytes + self.materials.nbytes + self.textures.nbytes
+        return (self.spheres.nbytes + self.quads.nbytes + self.materials.nbytes + self.textures.nbytes
                 + sum(im.nbytes for im in self.images))
 
     def sha256(self):
         h = hashlib.sha256()
-        for a in (self.spheres, self.materials, self.textures, *self.images):
+        for a in (self.spheres, self.quads, self.materials, self.textures, *self.images):
             h.update(a.tobytes())
         return h.hexdigest()
 
@@ -90,6 +108,94 @@ def _sph(c, r, material):
     s = np.zeros((), SPHERE_DT)
     s["cx"], s["cy"], s["cz"], s["r"], s["material"] = c[0], c[1], c[2], r, material
     return s
+
+
+def _quad(q, u, v, material):
+    r = np.zeros((), QUAD_DT)
+    r["q"], r["u"], r["v"], r["material"] = q, u, v, material
+    return r
+
+
+def box_quads(a, b, material):
+    """hittables.go:200-216 `Box(a, b, mat)`: the six quads, in the reference's order."""
+    a, b = np.asarray(a, F), np.asarray(b, F)
+    mn, mx = np.minimum(a, b), np.maximum(a, b)
+    dx, dy, dz = (F(mx[0] - mn[0]), 0, 0), (0, F(mx[1] - mn[1]), 0), (0, 0, F(mx[2] - mn[2]))
+    neg = lambda v: tuple(F(-1) * F(c) for c in v)  # noqa: E731  (Scale(v, -1))
+    return [
+        _quad((mn[0], mn[1], mx[2]), dx, dy, material),
+        _quad((mx[0], mn[1], mx[2]), neg(dz), dy, material),
+        _quad((mx[0], mn[1], mn[2]), neg(dx), dy, material),
+        _quad((mn[0], mn[1], mn[2]), dz, dy, material),
+        _quad((mn[0], mx[1], mx[2]), dx, neg(dz), material),
+        _quad((mn[0], mn[1], mn[2]), dx, dz, material),
+    ]
+
+
+def cornell_box_scene():
+    """main.go:194-225 — the scene main.go renders as checked in (main.go:55)."""
+    tex = [_tex(a=(.65, .05, .05)), _tex(a=(.73, .73, .73)), _tex(a=(.12, .45, .15)), _tex(a=(15, 15, 15))]
+    red, white, green, light = 0, 1, 2, 3
+    mats = [_mat(abi.RT_MAT_LAMBERTIAN, texture=0), _mat(abi.RT_MAT_LAMBERTIAN, texture=1),
+            _mat(abi.RT_MAT_LAMBERTIAN, texture=2), _mat(abi.RT_MAT_DIFFUSE_LIGHT, texture=3)]
+    quads = [
+        _quad((555, 0, 0), (0, 555, 0), (0, 0, 555), green),
+        _quad((0, 0, 0), (0, 555, 0), (0, 0, 555), red),
+        _quad((343, 554, 332), (-130, 0, 0), (0, 0, -105), light),
+        _quad((0, 0, 0), (555, 0, 0), (0, 0, 555), white),
+        _quad((555, 555, 555), (-555, 0, 0), (0, 0, -555), white),
+        _quad((0, 0, 555), (555, 0, 0), (0, 555, 0), white),
+    ]
+    quads += box_quads((130, 0, 65), (295, 165, 230), white)
+    quads += box_quads((265, 0, 295), (430, 330, 460), white)
+    return SceneData(np.zeros(0, SPHERE_DT), np.array(mats, MATERIAL_DT), np.array(tex, TEXTURE_DT),
+                     quads=np.array(quads, QUAD_DT), name="cornell")
+
+
+def cornell_camera_options(width=600, spp=200, max_depth=50):
+    """main.go:195-205."""
+    return camera_options(width, spp, max_depth, look_from=(278, 278, -800), look_at=(278, 278, 0), vfov_deg=40.0,
+                          defocus_deg=0.0, background=(0, 0, 0), aspect=1.0)
+
+
+def quad_demo_scene():
+    """main.go:132-160: five coloured quads."""
+    cols = [(1, .2, .2), (.2, 1, .2), (.2, .2, 1), (1, .5, 0), (.2, .8, .8)]
+    tex = [_tex(a=c) for c in cols]
+    mats = [_mat(abi.RT_MAT_LAMBERTIAN, texture=i) for i in range(5)]
+    quads = [
+        _quad((-3, -2, 5), (0, 0, -4), (0, 4, 0), 0),
+        _quad((-2, -2, 0), (4, 0, 0), (0, 4, 0), 1),
+        _quad((3, -2, 1), (0, 0, 4), (0, 4, 0), 2),
+        _quad((-2, 3, 1), (4, 0, 0), (0, 0, 4), 3),
+        _quad((-2, -3, 5), (4, 0, 0), (0, 0, -4), 4),
+    ]
+    return SceneData(np.zeros(0, SPHERE_DT), np.array(mats, MATERIAL_DT), np.array(tex, TEXTURE_DT),
+                     quads=np.array(quads, QUAD_DT), name="quads")
+
+
+def quad_demo_camera_options(width=400, spp=100):
+    """main.go:133-143."""
+    return camera_options(width, spp, look_from=(0, 0, 9), look_at=(0, 0, 0), vfov_deg=80.0, defocus_deg=0.0)
+
+
+def mixed_scene():
+    """Spheres and quads interleaved in World order (exercises object IDs across both kinds): a lit
+    room of quads with a glass, a metal and a diffuse sphere in it."""
+    tex = [_tex(a=(.73, .73, .73)), _tex(a=(7, 7, 7)), _tex(abi.RT_TEX_CHECKER, a=(.2, .3, .1), b=(.9, .9, .9), scale=40.0),
+           _tex(a=(.65, .05, .05))]
+    mats = [_mat(abi.RT_MAT_LAMBERTIAN, texture=0), _mat(abi.RT_MAT_DIFFUSE_LIGHT, texture=1),
+            _mat(abi.RT_MAT_LAMBERTIAN, texture=2), _mat(abi.RT_MAT_DIELECTRIC, ior=1.5),
+            _mat(abi.RT_MAT_METAL, albedo=(.8, .85, .88), fuzz=0.05), _mat(abi.RT_MAT_LAMBERTIAN, texture=3)]
+    quads = [
+        _quad((0, 0, 0), (555, 0, 0), (0, 0, 555), 2),        # floor (checker)        id 0
+        _quad((213, 554, 227), (130, 0, 0), (0, 0, 105), 1),  # light                  id 2
+        _quad((0, 0, 555), (555, 0, 0), (0, 555, 0), 0),      # back wall              id 3
+        _quad((0, 555, 0), (555, 0, 0), (0, 0, 555), 0),      # ceiling                id 5
+    ]
+    spheres = [_sph((190, 90, 190), 90, 3), _sph((400, 120, 300), 120, 4), _sph((300, 60, 120), 60, 5)]  # ids 1, 4, 6
+    return SceneData(np.array(spheres, SPHERE_DT), np.array(mats, MATERIAL_DT), np.array(tex, TEXTURE_DT),
+                     quads=np.array(quads, QUAD_DT), sphere_ids=[1, 4, 6], quad_ids=[0, 2, 3, 5], name="mixed")
 
 
 def random_scene(half=11, seed=SCENE_SEED_RANDOM, exclude=(), name="random"):
@@ -263,6 +369,8 @@ CONFIGS = {
     "C3": dict(scene="earth+random", width=1920, spp=256),
     "C4": dict(scene="stress", width=1920, spp=64),
     "C5": dict(scene="random", width=3840, spp=4096),
+    # not a BASELINE.json config: the scene main.go renders as checked in (main.go:55, 194-225)
+    "CB": dict(scene="cornell", width=600, spp=200),
 }
 
 
@@ -275,6 +383,9 @@ def build_config(name, width=None, spp=None, stress_half=500):
     if cfg["scene"] == "random":
         scene = random_scene()
         cam = camera_options(cfg["width"], cfg["spp"])
+    elif cfg["scene"] == "cornell":
+        scene = cornell_box_scene()
+        cam = cornell_camera_options(cfg["width"], cfg["spp"])
     elif cfg["scene"] == "earth+random":
         scene = earth_random_scene()
         cam = camera_options(cfg["width"], cfg["spp"])

@@ -13,6 +13,7 @@
 
 namespace {
 struct HostScene {
+    ScenePrims prims;
     FlatBvh bvh;
     std::vector<F4> mats;
     std::vector<DevImage> images;
@@ -21,9 +22,10 @@ struct HostScene {
 
 void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *s) {
     double m[3], ext;
-    compute_scene_center(d->spheres, d->n_spheres, m, &ext);
+    load_scene_prims(d, &s->prims);
+    compute_scene_center(s->prims, m, &ext);
     float R = origin_radius > 0 ? origin_radius : (d->ray_origin_radius > 0 ? d->ray_origin_radius : (float)(2 * ext));
-    build_flat_bvh(d->spheres, d->n_spheres, R, max_leaf, &s->bvh);
+    build_flat_bvh(s->prims, R, max_leaf, &s->bvh);
     pack_materials(d, &s->mats);
     s->images.resize(d->n_images);
     s->texels.resize(d->n_images);
@@ -35,6 +37,16 @@ void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *
             for (int c = 0; c < 3; c++) s->texels[i][4 * k + c] = im.rgb16[3 * k + c];
         s->images[i].texels = s->texels[i].data(), s->images[i].w = im.w, s->images[i].h = im.h;
     }
+}
+// Emit + Scatter at a HitRec (sphere or quad slot), like the kernel does.
+bool shade_at(const HostScene &s, const HitRec &h, PathRng &rng, V3 &o, V3 &dir, V3 &atten, V3 &emitted) {
+    if (h.slot & RT_HIT_QUAD) {
+        const F4 *q = s.bvh.quad.data() + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
+        const uint32_t mi = as_uint(q[1].w);
+        return shade_hit_quad(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), q, h.t, rng, o, dir, atten, emitted);
+    }
+    const int mi = s.bvh.meta[h.slot].y;
+    return shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[h.slot], h.t, rng, o, dir, atten, emitted);
 }
 } // namespace
 
@@ -58,11 +70,12 @@ int hs_trace(const rt_scene_desc *d, int max_leaf, float origin_radius, const fl
     for (int64_t i = 0; i < n; i++) {
         LocalStack<64> stack;
         HitRec h;
-        trace_closest<LocalStack<64>, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
-                                            v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
-                                            v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmin, tmax, stack, h, &wc);
+        trace_closest<LocalStack<64>, true, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
+                                                  v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+                                                  v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmin, tmax, stack, h, &wc,
+                                                  s.bvh.quad.data());
         if (h.slot == RT_REF_NONE) id_out[i] = -1, t_out[i] = 0;
-        else id_out[i] = s.bvh.meta[h.slot].x, t_out[i] = h.t;
+        else id_out[i] = slot_object_id(h.slot, s.bvh.meta.data(), s.bvh.quad.data()), t_out[i] = h.t;
     }
     if (box_tests) *box_tests = wc.box_tests;
     if (sphere_tests) *sphere_tests = wc.sphere_tests;
@@ -87,16 +100,15 @@ int hs_render(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32
             for (int depth = 0; depth < c.max_depth;) {
                 LocalStack<64> stack;
                 HitRec h;
-                trace_closest<LocalStack<64>, false>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
-                                                     s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, nullptr);
+                trace_closest<LocalStack<64>, false, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
+                                                           s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, nullptr,
+                                                           s.bvh.quad.data());
                 if (h.slot == RT_REF_NONE) {
                     rad = rad + thr * c.background;
                     break;
                 }
-                const int mi = s.bvh.meta[h.slot].y;
                 V3 atten, emitted;
-                bool sc = shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[h.slot], h.t, rng, o,
-                                    dir, atten, emitted);
+                bool sc = shade_at(s, h, rng, o, dir, atten, emitted);
                 rad = rad + thr * emitted;
                 if (!sc) break;
                 thr = thr * atten;

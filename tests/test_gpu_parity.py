@@ -267,3 +267,63 @@ def test_host_mirrors_write_the_reference_ppm(gpu, orc, tmp_path):
     rgb = np.array([[int(v) for v in l.split()] for l in lines[3:-1]], np.uint8).reshape(90, 160, 3)
     rrgb, _, _ = orc.render(api.flatten_world(world), cam.c, SEED, order=orc.ORDER_ITERATIVE)
     assert (rgb != rrgb).any(-1).mean() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["cornell", "quads", "mixed"])
+def test_quad_scenes_match_oracle(gpu, orc, name):
+    """SURVEY §8f rank 1 — Quad / Box / DiffuseLight: main.go's cornellBox (the scene it renders as
+    checked in, main.go:55) and quadDemo, plus a mixed sphere+quad world with interleaved IDs."""
+    if name == "cornell":
+        s, o = scenes.cornell_box_scene(), scenes.cornell_camera_options(200, 16)
+    elif name == "quads":
+        s, o = scenes.quad_demo_scene(), scenes.quad_demo_camera_options(240, 8)
+    else:
+        s, o = scenes.mixed_scene(), scenes.cornell_camera_options(160, 16)
+    cam = api.camera_from_options(o)
+    ro, rd = orc.primary_rays(cam, SEED, 0, cam.width * cam.height, 0, 1)
+    rng = np.random.default_rng(4)
+    so = (rng.uniform(5, 550, size=(200_000, 3)) if name != "quads" else rng.uniform(-3, 5, size=(200_000, 3))).astype(np.float32)
+    sd = rng.normal(size=(200_000, 3)).astype(np.float32)
+    o_all, d_all = np.concatenate([ro, so]), np.concatenate([rd, sd])
+    with api.Scene(s) as sc:
+        ids, ts = sc.trace(o_all, d_all)
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    rids, rts = orc.trace(s, o_all, d_all)
+    assert np.array_equal(ids, rids)
+    assert np.array_equal(ts[rids >= 0].view(np.uint32), rts[rids >= 0].view(np.uint32))
+    rrgb, racc, rst = orc.render(s, cam, SEED, order=orc.ORDER_ITERATIVE)
+    same = (acc.view(np.uint32) == racc.view(np.uint32)).all(-1)
+    assert same.mean() > 0.9999 and (rgb != rrgb).any(-1).mean() < 1e-4
+    assert abs(int(st.rays) - int(rst.rays)) <= 1e-4 * rst.rays
+    if name != "quads":
+        assert acc.max() / cam.spp > 5  # the light is seen directly
+
+
+def test_cornell_through_the_mirror_api(gpu, orc):
+    """main.go:194-225 written against the Python mirror (NewQuad, Box, NewDiffuseLight) renders
+    the same image as the flat scene through the oracle."""
+    import io
+    world = api.NewWorld()
+    red = api.NewLambertian(api.NewSolidColor(.65, .05, .05))
+    white = api.NewLambertian(api.NewSolidColor(.73, .73, .73))
+    green = api.NewLambertian(api.NewSolidColor(.12, .45, .15))
+    light = api.NewDiffuseLight(api.NewSolidColor(15, 15, 15))
+    V = api.NewVec3
+    world.Add(api.NewQuad(V(555, 0, 0), V(0, 555, 0), V(0, 0, 555), green))
+    world.Add(api.NewQuad(V(0, 0, 0), V(0, 555, 0), V(0, 0, 555), red))
+    world.Add(api.NewQuad(V(343, 554, 332), V(-130, 0, 0), V(0, 0, -105), light))
+    world.Add(api.NewQuad(V(0, 0, 0), V(555, 0, 0), V(0, 0, 555), white))
+    world.Add(api.NewQuad(V(555, 555, 555), V(-555, 0, 0), V(0, 0, -555), white))
+    world.Add(api.NewQuad(V(0, 0, 555), V(555, 0, 0), V(0, 555, 0), white))
+    world.Add(api.Box(V(130, 0, 65), V(295, 165, 230), white))
+    world.Add(api.Box(V(265, 0, 295), V(430, 330, 460), white))
+    cam = api.NewCamera(1, 120, api.WithSamplesPerPixel(8), api.WithMaxRayDepth(50), api.WithLookFrom(V(278, 278, -800)),
+                        api.WithLookAt(V(278, 278, 0)), api.WithFOVDegrees(40), api.WithDefocusAngleDegrees(0),
+                        api.WithBackgroundColor(api.NewVec3Zero()))
+    buf = io.StringIO()
+    cam.Render(api.NewBVHFromWorld(world), buf)
+    lines = buf.getvalue().split("\\n")
+    assert lines[:3] == ["P3", "120 120", "255"]
+    rgb = np.array([[int(v) for v in l.split()] for l in lines[3:-1]], np.uint8).reshape(120, 120, 3)
+    rrgb, _, _ = orc.render(scenes.cornell_box_scene(), cam.c, SEED, order=orc.ORDER_ITERATIVE)
+    assert (rgb != rrgb).any(-1).mean() < 1e-3

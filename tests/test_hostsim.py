@@ -122,3 +122,57 @@ def test_image_texture_path_equals_oracle(hs, orc):
     # the out-of-bounds colour (0, 0.529, 0) shows up on ~5/24 of the longitudes
     green = (racc[..., 1] > 0.3) & (racc[..., 0] == 0) & (racc[..., 2] == 0)
     assert green.mean() > 0.005
+
+
+def _hs_render(hs, scene, cam, seed, spp):
+    desc, keep = scene.to_desc()
+    rgb = np.zeros((cam.height, cam.width, 3), np.uint8)
+    acc = np.zeros((cam.height, cam.width, 3), np.float32)
+    hs.hs_render(C.byref(desc), C.byref(cam), C.c_uint64(seed), 0, spp, spp, 4, rgb.ctypes.data_as(C.c_void_p),
+                 acc.ctypes.data_as(C.c_void_p))
+    return rgb, acc
+
+
+@pytest.mark.parametrize("name", ["cornell", "quads", "mixed"])
+def test_quad_scenes_equal_oracle(hs, orc, name):
+    """Quad / Box / DiffuseLight scenes (main.go:132-160, 194-225) and a mixed sphere+quad world:
+    closest hits (object IDs across both kinds) and the rendered sums equal the oracle's."""
+    if name == "cornell":
+        s, o = scenes.cornell_box_scene(), scenes.cornell_camera_options(64, 8)
+    elif name == "quads":
+        s, o = scenes.quad_demo_scene(), scenes.quad_demo_camera_options(96, 4)
+    else:
+        s, o = scenes.mixed_scene(), scenes.cornell_camera_options(64, 8)
+    cam = orc.camera_from_options(o)
+    ro, rd = orc.primary_rays(cam, 5, 0, cam.width * cam.height, 0, 1)
+    rng = np.random.default_rng(2)
+    so = rng.uniform(5, 550, size=(20000, 3)).astype(np.float32) if name != "quads" else rng.uniform(-3, 5, size=(20000, 3)).astype(np.float32)
+    sd = rng.normal(size=(20000, 3)).astype(np.float32)
+    o_all, d_all = np.concatenate([ro, so]), np.concatenate([rd, sd])
+    ids, ts, _, _ = hs_trace(hs, s, o_all, d_all)
+    rids, rts = orc.trace(s, o_all, d_all)
+    assert np.array_equal(ids, rids)
+    assert np.array_equal(ts[rids >= 0].view(np.uint32), rts[rids >= 0].view(np.uint32))
+    assert (rids >= 0).mean() > 0.15
+    rgb, acc = _hs_render(hs, s, cam, 11, cam.spp)
+    rrgb, racc, _ = orc.render(s, cam, 11, order=orc.ORDER_ITERATIVE)
+    assert np.array_equal(acc.view(np.uint32), racc.view(np.uint32))
+    assert np.array_equal(rgb, rrgb)
+    if name != "quads":
+        assert acc.max() > 5  # the light is seen
+
+
+def test_quad_edge_cases(hs, orc):
+    """Edges are inside (alpha, beta in [0,1]), parallel rays miss, coincident quads: lower ID wins."""
+    tex, mat = np.zeros(1, scenes.TEXTURE_DT), np.zeros(1, scenes.MATERIAL_DT)
+    q = np.zeros(3, scenes.QUAD_DT)
+    q[0] = ((-1, -1, -2), (2, 0, 0), (0, 2, 0), 0)
+    q[1] = ((-1, -1, -2), (2, 0, 0), (0, 2, 0), 0)   # coincident twin
+    q[2] = ((-1, -1, -5), (2, 0, 0), (0, 2, 0), 0)
+    s = scenes.SceneData(np.zeros(0, scenes.SPHERE_DT), mat, tex, quads=q)
+    o = np.zeros((6, 3), np.float32)
+    d = np.array([[0, 0, -1], [1, 1, -2], [1.001, 0, -2], [1, 0, 0], [0, 0, 1], [2.4, 2.4, -5]], np.float32)
+    ids, ts, _, _ = hs_trace(hs, s, o, d)
+    rids, rts = orc.trace(s, o, d)
+    assert np.array_equal(ids, rids) and ids.tolist() == [0, 0, -1, -1, -1, 0]
+    assert ts[0] == 2.0 and ts[1] == 1.0 and np.array_equal(ts[rids >= 0], rts[rids >= 0])

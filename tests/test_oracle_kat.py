@@ -272,3 +272,46 @@ def test_reference_bvh_equals_linear_list(orc):
         assert (ids != i2).mean() < 1e-4
         same = ids == i2
         assert np.array_equal(ts[same], t2[same])
+
+
+def test_quad_hit(orc):
+    """hittables.go:149-190: Q=(-1,-1,-2), u=(2,0,0), v=(0,2,0); o=0, d=(0,0,-1) -> t=2, alpha=beta=0.5."""
+    tex, mat = np.zeros(1, scenes.TEXTURE_DT), np.zeros(1, scenes.MATERIAL_DT)
+    q = np.zeros(1, scenes.QUAD_DT)
+    q[0] = ((-1, -1, -2), (2, 0, 0), (0, 2, 0), 0)
+    s = scenes.SceneData(np.zeros(0, scenes.SPHERE_DT), mat, tex, quads=q)
+    h = orc.hit_info(s, (0, 0, 0), (0, 0, -1))
+    assert h["id"] == 0 and h["t"] == 2.0 and h["u"] == 0.5 and h["v"] == 0.5
+    assert h["normal"].tolist() == [0, 0, 1] and h["front_face"]      # n = u x v = +z, ray along -z
+    assert orc.hit_info(s, (0, 0, 0), (1.01, 0, -2)) is None           # alpha > 1: outside (InPlane)
+    assert orc.hit_info(s, (0, 0, 0), (1.0, 1.0, -2))["u"] == 1.0      # the edge is inside
+    assert orc.hit_info(s, (0, 0, 0), (1, 0, 0)) is None               # parallel: |denom| < 1e-8
+    back = orc.hit_info(s, (0, 0, -4), (0, 0, 1))
+    assert back["t"] == 2.0 and not back["front_face"] and back["normal"].tolist() == [0, 0, -1]
+
+
+def test_mixed_world_object_ids(orc):
+    """Object ID = position in World.hittables across spheres and quads; first object wins ties."""
+    m = scenes.mixed_scene()
+    o = [(100, 300, 400), (190, 400, 190), (278, 278, -800), (278, 100, 278)]
+    d = [(0, -1, 0), (0, -1, 0), (0, 0, 1), (0, 1, 0)]
+    ids, ts = orc.trace(m, o, d)
+    assert ids.tolist() == [0, 1, 3, 2]        # floor quad, glass sphere from above, back wall, light
+    assert ts.tolist() == [300.0, 220.0, 1355.0, 454.0]
+    i2, _ = orc.trace(m, o, d, mode=orc.MODE_REF_BVH)
+    assert np.array_equal(ids, i2)
+
+
+def test_cornell_box_renders(orc):
+    """main.go:194-225: emissive quad lights a closed box; background is black."""
+    s = scenes.cornell_box_scene()
+    cam = orc.camera_from_options(scenes.cornell_camera_options(48, 32))
+    assert (cam.width, cam.height) == (48, 48)
+    rgb, acc, st = orc.render(s, cam, 3)
+    mean = acc / 32
+    assert mean.max() == 15.0                                   # the light seen directly (15,15,15)
+    assert 0.3 < (acc > 0).any(-1).mean() < 0.98                # noisy but lit; black background never adds
+    left, right = mean[:, :8].reshape(-1, 3).mean(0), mean[:, -8:].reshape(-1, 3).mean(0)
+    assert left[1] > left[0] and right[0] > right[1]            # green wall at image-left, red at image-right
+    r2, a2, _ = orc.render(s, cam, 3, mode=orc.MODE_REF_BVH)
+    assert (np.abs(a2 - acc) > 1e-3).any(-1).mean() < 0.01
