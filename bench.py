@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
 
 def config_dict(args, cam_opts, scene, world):
     cam_w = cam_opts.image_width
-    return {"workload": f"{args.config}: {scene.name} scene, {len(scene.spheres)} spheres, {cam_w} px wide 16:9, "
+    return {"workload": f"{args.config}: {scene.name} scene, {scene.n_objects()} hittables, {cam_w} px wide, "
                         f"{cam_opts.spp} spp/GPU, depth {cam_opts.max_depth}",
             "spheres": int(len(scene.spheres)), "quads": int(len(scene.quads)), "width": int(cam_w), "spp_per_gpu": int(cam_opts.spp),
             "max_depth": int(cam_opts.max_depth), "parallelism": f"sample-split x{world}" if world > 1 else "single GPU",

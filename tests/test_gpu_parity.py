@@ -322,7 +322,7 @@ def test_cornell_through_the_mirror_api(gpu, orc):
                         api.WithBackgroundColor(api.NewVec3Zero()))
     buf = io.StringIO()
     cam.Render(api.NewBVHFromWorld(world), buf)
-    lines = buf.getvalue().split("\\n")
+    lines = buf.getvalue().split("\n")
     assert lines[:3] == ["P3", "120 120", "255"]
     rgb = np.array([[int(v) for v in l.split()] for l in lines[3:-1]], np.uint8).reshape(120, 120, 3)
     rrgb, _, _ = orc.render(scenes.cornell_box_scene(), cam.c, SEED, order=orc.ORDER_ITERATIVE)
