@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -49,7 +49,8 @@ typedef enum rt_material_kind {
 typedef enum rt_texture_kind {
     RT_TEX_SOLID = 0,   /* materials.go:155-157 */
     RT_TEX_CHECKER = 1, /* materials.go:127-137 */
-    RT_TEX_IMAGE = 2    /* materials.go:175-193 */
+    RT_TEX_IMAGE = 2,   /* materials.go:175-193 */
+    RT_TEX_NOISE = 3    /* materials.go:280-295: marble from Perlin turbulence */
 } rt_texture_kind;
 
 /* hittables.go:78-83 `Sphere{Center, Radius, Material}`; the bounding box (hittables.go:91) is
@@ -82,8 +83,8 @@ typedef struct rt_texture {
     uint32_t kind;  /* rt_texture_kind                                                     */
     float a[3];     /* SolidColor.albedo (materials.go:152) or Checkered.even (:123)       */
     float b[3];     /* Checkered.odd (:124)                                                */
-    float scale;    /* Checkered.scale (:122)                                              */
-    uint32_t image; /* ImageTexture: index into images                                     */
+    float scale;    /* Checkered.scale (:122) or NoiseTexture.scale (:282)                 */
+    uint32_t image; /* ImageTexture: index into images; NoiseTexture: index into perlins   */
     float oob[3];   /* ImageTexture: colour Go's img.At() returns outside Bounds(), i.e.
                        img.At(W,0).RGBA()/65535 evaluated once by the bridge */
 } rt_texture;
@@ -94,6 +95,14 @@ typedef struct rt_image {
     int32_t w, h;
     const uint16_t *rgb16;
 } rt_image;
+
+/* Perlin's tables (materials.go:195-200, built by NewPerlin :202-216): 256 gradient vectors in
+ * [-1,1)^3 (not normalised) and three permutations of 0..255.  The bridge copies them from the Go
+ * object, so the device evaluates the very noise field the Go scene holds. */
+typedef struct rt_perlin {
+    float vec[256][3];
+    uint8_t perm_x[256], perm_y[256], perm_z[256];
+} rt_perlin;
 
 typedef struct rt_scene_desc {
     uint32_t abi_version; /* RT_B200_ABI_VERSION */
@@ -119,6 +128,9 @@ typedef struct rt_scene_desc {
     uint64_t n_quads;
     const uint32_t *sphere_ids;
     const uint32_t *quad_ids;
+    const rt_perlin *perlins; /* NoiseTexture.perlin, indexed by rt_texture.image */
+    uint32_t n_perlins;
+    uint32_t reserved2;
 } rt_scene_desc;
 
 /* The derived Camera fields of camera.go:23-52 as computed by Camera.init (camera.go:128-166).

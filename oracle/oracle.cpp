@@ -338,6 +338,7 @@ struct Scene {
         std::vector<uint16_t> px;
     };
     std::vector<Img> images;
+    std::vector<rt_perlin> perlins;
     uint32_t material_of(int32_t object) const {
         const Prim &p = prims[object];
         return p.kind == 0 ? spheres[p.index].material : quads[p.index].material;
@@ -377,6 +378,7 @@ bool load_scene(const rt_scene_desc *d, Scene *s) {
         im.px.assign(d->images[i].rgb16, d->images[i].rgb16 + np);
         s->images.push_back(std::move(im));
     }
+    if (d->n_perlins) s->perlins.assign(d->perlins, d->perlins + d->n_perlins);
     for (size_t i = 0; i < n; i++)
         if (s->material_of((int32_t)i) >= s->materials.size()) return false;
     for (auto &m : s->materials)
@@ -384,7 +386,9 @@ bool load_scene(const rt_scene_desc *d, Scene *s) {
             m.texture >= s->textures.size())
             return false;
     for (auto &t : s->textures)
-        if (t.kind == RT_TEX_IMAGE && t.image >= s->images.size()) return false;
+        if ((t.kind == RT_TEX_IMAGE && t.image >= s->images.size()) ||
+            (t.kind == RT_TEX_NOISE && t.image >= s->perlins.size()))
+            return false;
     return true;
 }
 
@@ -540,9 +544,65 @@ inline V3 image_texture(const Scene &sc, const rt_texture &t, float u, float v) 
     float col_scale = (float)(1.0 / 65535.0);
     return v3((float)px[0] * col_scale, (float)px[1] * col_scale, (float)px[2] * col_scale);
 }
+// math.go:58-60
+inline float lerp1(float t, float x, float y) { return x * (1 - t) + y * t; }
+// math.go:78-82
+inline float bilerp(float tx, float ty, float c00, float c10, float c01, float c11) {
+    float a = lerp1(tx, c00, c10);
+    float b = lerp1(tx, c01, c11);
+    return lerp1(ty, a, b);
+}
+// math.go:84-92
+inline float trilerp(float tx, float ty, float tz, float c000, float c100, float c010, float c110, float c001,
+                     float c101, float c011, float c111) {
+    float e = bilerp(tx, ty, c000, c100, c010, c110);
+    float f = bilerp(tx, ty, c001, c101, c011, c111);
+    return lerp1(tz, e, f);
+}
+// materials.go:218-220
+inline float smoothstep(float t) { return t * t * (3 - 2 * t); }
+// materials.go:223-249
+inline float perlin_noise(const rt_perlin &per, V3 p) {
+    float xi = (float)std::floor((double)p.x), yi = (float)std::floor((double)p.y), zi = (float)std::floor((double)p.z);
+    float tx = p.x - xi, ty = p.y - yi, tz = p.z - zi;
+    int rx0 = (int)((long long)xi & 255), rx1 = (rx0 + 1) & 255;
+    int ry0 = (int)((long long)yi & 255), ry1 = (ry0 + 1) & 255;
+    int rz0 = (int)((long long)zi & 255), rz1 = (rz0 + 1) & 255;
+    auto g = [&](int ix, int iy, int iz) {
+        const float *q = per.vec[per.perm_x[ix] ^ per.perm_y[iy] ^ per.perm_z[iz]];
+        return v3(q[0], q[1], q[2]);
+    };
+    float c000 = dot(g(rx0, ry0, rz0), v3(tx, ty, tz));
+    float c001 = dot(g(rx0, ry0, rz1), v3(tx, ty, tz - 1));
+    float c010 = dot(g(rx0, ry1, rz0), v3(tx, ty - 1, tz));
+    float c011 = dot(g(rx0, ry1, rz1), v3(tx, ty - 1, tz - 1));
+    float c100 = dot(g(rx1, ry0, rz0), v3(tx - 1, ty, tz));
+    float c101 = dot(g(rx1, ry0, rz1), v3(tx - 1, ty, tz - 1));
+    float c110 = dot(g(rx1, ry1, rz0), v3(tx - 1, ty - 1, tz));
+    float c111 = dot(g(rx1, ry1, rz1), v3(tx - 1, ty - 1, tz - 1));
+    return trilerp(smoothstep(tx), smoothstep(ty), smoothstep(tz), c000, c100, c010, c110, c001, c101, c011, c111);
+}
+// materials.go:251-262
+inline float perlin_turb(const rt_perlin &per, V3 p, int depth) {
+    float sum = 0, weight = 1.0f;
+    for (int i = 0; i < depth; i++) {
+        sum += weight * perlin_noise(per, p);
+        weight *= 0.5f;
+        p = scale(p, 2);
+    }
+    return (float)std::fabs((double)sum);
+}
+// materials.go:285-288
+inline V3 noise_texture(const Scene &sc, const rt_texture &t, V3 point) {
+    point = scale(point, t.scale);
+    float s = 0.5f * (1 + (float)std::sin((double)(point.z + 10 * perlin_turb(sc.perlins[t.image], point, 7))));
+    return scale(v3(1, 1, 1), s);
+}
+
 inline V3 texture_value(const Scene &sc, uint32_t tex, float u, float v, V3 p) {
     const rt_texture &t = sc.textures[tex];
     switch (t.kind) {
+    case RT_TEX_NOISE: return noise_texture(sc, t, p);
     case RT_TEX_CHECKER: return checker_texture(t, p);
     case RT_TEX_IMAGE: return image_texture(sc, t, u, v);
     default: return v3(t.a[0], t.a[1], t.a[2]); // materials.go:155-157

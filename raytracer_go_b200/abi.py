@@ -5,7 +5,7 @@ sizes/offsets against the compiled library's view where that is observable.
 """
 import ctypes as C
 
-RT_B200_ABI_VERSION = 2
+RT_B200_ABI_VERSION = 3
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1
@@ -15,7 +15,7 @@ RT_ERR_OUT_OF_MEMORY = -4
 RT_ERR_UNSUPPORTED = -5
 
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT = 0, 1, 2, 3
-RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE = 0, 1, 2
+RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = 0, 1, 2, 3
 
 RT_FLAG_NONE = 0
 RT_FLAG_COUNT_WORK = 1
@@ -46,6 +46,11 @@ class rt_image(C.Structure):
     _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("rgb16", C.POINTER(C.c_uint16))]
 
 
+class rt_perlin(C.Structure):
+    _fields_ = [("vec", (C.c_float * 3) * 256), ("perm_x", C.c_uint8 * 256), ("perm_y", C.c_uint8 * 256),
+                ("perm_z", C.c_uint8 * 256)]
+
+
 class rt_scene_desc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("reserved", C.c_uint32),
                 ("spheres", C.POINTER(rt_sphere)), ("n_spheres", C.c_uint64),
@@ -54,7 +59,8 @@ class rt_scene_desc(C.Structure):
                 ("images", C.POINTER(rt_image)), ("n_images", C.c_uint32),
                 ("ray_origin_radius", C.c_float),
                 ("quads", C.POINTER(rt_quad)), ("n_quads", C.c_uint64),
-                ("sphere_ids", C.POINTER(C.c_uint32)), ("quad_ids", C.POINTER(C.c_uint32))]
+                ("sphere_ids", C.POINTER(C.c_uint32)), ("quad_ids", C.POINTER(C.c_uint32)),
+                ("perlins", C.POINTER(rt_perlin)), ("n_perlins", C.c_uint32), ("reserved2", C.c_uint32)]
 
 
 class rt_camera(C.Structure):

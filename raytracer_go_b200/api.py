@@ -161,6 +161,18 @@ def NewImageTexture(img, oob=scenes.JPEG_OOB):
     return ImageTexture(img, oob)
 
 
+class NoiseTexture:  # materials.go:280-295
+    """perlin: a scenes.PERLIN_DT record (NewPerlin's tables, materials.go:202-216)."""
+
+    def __init__(self, perlin, scale):
+        self.perlin, self.scale = perlin, F(scale)
+
+
+def NewNoiseTexture(seed, scale):
+    """The reference takes a *rand.Rand (clock-seeded, main.go:120-123); here a seed."""
+    return NoiseTexture(scenes.new_perlin(seed), scale)
+
+
 class Lambertian:  # materials.go:19-31
     def __init__(self, albedo):
         self.albedo = albedo
@@ -261,7 +273,7 @@ def flatten_world(world):
     """World/BVH -> scenes.SceneData: materials and textures de-duplicated by identity, spheres in
     insertion order.  This is the walk the cgo bridge performs."""
     tex_index, mat_index = {}, {}
-    textures, materials, images = [], [], []
+    textures, materials, images, perlins = [], [], [], []
     spheres, quads, sphere_ids, quad_ids = [], [], [], []
 
     def tex_id(t):
@@ -275,6 +287,9 @@ def flatten_world(world):
             images.append(t.img)
         elif isinstance(t, SolidColor):
             rec["kind"], rec["a"] = abi.RT_TEX_SOLID, t.albedo
+        elif isinstance(t, NoiseTexture):
+            rec["kind"], rec["scale"], rec["image"] = abi.RT_TEX_NOISE, t.scale, len(perlins)
+            perlins.append(t.perlin)
         else:
             raise TypeError(f"texture {type(t).__name__} is outside the accelerated path")
         textures.append(rec)
@@ -312,7 +327,8 @@ def flatten_world(world):
                             np.array(materials, scenes.MATERIAL_DT).reshape(-1),
                             np.array(textures, scenes.TEXTURE_DT).reshape(-1), images,
                             quads=np.array(quads, scenes.QUAD_DT).reshape(-1),
-                            sphere_ids=sphere_ids, quad_ids=quad_ids)
+                            sphere_ids=sphere_ids, quad_ids=quad_ids,
+                            perlins=np.array(perlins, scenes.PERLIN_DT).reshape(-1))
 
 
 # CameraOpt functional options, camera.go:54-102

@@ -376,6 +376,9 @@ void pack_materials(const rt_scene_desc *d, std::vector<F4> *out) {
                 m0.x = t.a[0], m0.y = t.a[1], m0.z = t.a[2];
                 m0.w = 1 / t.scale; // materials.go:128
                 m1.x = t.b[0], m1.y = t.b[1], m1.z = t.b[2];
+            } else if (t.kind == RT_TEX_NOISE) {
+                code = RT_CODE(m.kind, t.kind, t.image); // index into the Perlin tables
+                m0.w = t.scale;                            // NoiseTexture.scale, materials.go:282
             } else if (t.kind == RT_TEX_IMAGE) {
                 m0.x = t.oob[0], m0.y = t.oob[1], m0.z = t.oob[2];
             } else {

@@ -66,7 +66,7 @@ struct DevScene {
     const F4 *sph;
     const I2 *meta;
     const F4 *mats;
-    const DevImage *images;
+    DevTex tex;      // images and Perlin tables (global memory)
     const F4 *quads; // RT_QUAD_F4 x F4 per quad slot
     uint32_t root_ref, n_nodes, n_slots, n_mats, n_quad_slots;
     uint32_t stack_depth; // entries per thread for the shared-memory stack
@@ -217,12 +217,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                 const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
                 const uint32_t mi = __float_as_uint(q[1].w);
                 const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
-                scattered = shade_hit_quad(m0, m1, p.sc.images, q, h.t, rng, o, d, atten, emitted);
+                scattered = shade_hit_quad(m0, m1, p.sc.tex, q, h.t, rng, o, d, atten, emitted);
             } else {
                 const F4 s = sph[h.slot];
                 const int mi = meta[h.slot].y;
                 const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
-                scattered = shade_hit(m0, m1, p.sc.images, s, h.t, rng, o, d, atten, emitted);
+                scattered = shade_hit(m0, m1, p.sc.tex, s, h.t, rng, o, d, atten, emitted);
             }
             rad = rad + thr * emitted; // ray.go:41,50
             if (!scattered) {
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(BLOCK, 1) render_pool_kernel(const __grid_cons
                     rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + ks);
                     rng.block = blk[k];
                     V3 atten, emitted;
-                    const bool scattered = shade_hit(m0, m1, p.sc.images, s, A.w, rng, o, d, atten, emitted);
+                    const bool scattered = shade_hit(m0, m1, p.sc.tex, s, A.w, rng, o, d, atten, emitted);
                     blk[k] = rng.block;
                     rad[k] = rad[k] + thr[k] * emitted; // ray.go:41,50
                     if (!scattered) {
@@ -633,6 +633,7 @@ struct rt_scene {
     bool has_quads = false;
     I2 *d_meta = nullptr;
     DevImage *d_images = nullptr;
+    DevPerlin *d_perlins = nullptr;
     std::vector<uint16_t *> d_texels;
     int grid_cache[2] = {0, 0};  // persistent grid size of the plain / counting megakernel
     size_t smem_cache[2] = {0, 0};
@@ -684,7 +685,7 @@ static int validate_desc(const rt_scene_desc *d) {
     if (d->abi_version != RT_B200_ABI_VERSION)
         return fail(RT_ERR_INVALID_ARGUMENT, "abi_version %u != %d", d->abi_version, RT_B200_ABI_VERSION);
     if ((d->n_spheres && !d->spheres) || (d->n_materials && !d->materials) || (d->n_textures && !d->textures) ||
-        (d->n_images && !d->images))
+        (d->n_images && !d->images) || (d->n_perlins && !d->perlins))
         return fail(RT_ERR_INVALID_ARGUMENT, "null array with non-zero count");
     if (d->n_quads && !d->quads) return fail(RT_ERR_INVALID_ARGUMENT, "null array with non-zero count");
     if (d->n_spheres >= (1ull << 27) || d->n_quads >= (1ull << 27))
@@ -715,7 +716,9 @@ static int validate_desc(const rt_scene_desc *d) {
     }
     for (uint32_t i = 0; i < d->n_textures; i++) {
         const rt_texture &t = d->textures[i];
-        if (t.kind > RT_TEX_IMAGE) return fail(RT_ERR_UNSUPPORTED, "texture %u: unknown kind %u", i, t.kind);
+        if (t.kind > RT_TEX_NOISE) return fail(RT_ERR_UNSUPPORTED, "texture %u: unknown kind %u", i, t.kind);
+        if (t.kind == RT_TEX_NOISE && t.image >= d->n_perlins)
+            return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: perlin table %u out of range", i, t.image);
         if (t.kind == RT_TEX_IMAGE && t.image >= d->n_images)
             return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: image %u out of range", i, t.image);
     }
@@ -729,7 +732,7 @@ static void free_scene(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaFree(s->d_nodes), cudaFree(s->d_sph), cudaFree(s->d_mats), cudaFree(s->d_meta), cudaFree(s->d_images);
-    cudaFree(s->d_quads);
+    cudaFree(s->d_quads), cudaFree(s->d_perlins);
     for (auto p : s->d_texels) cudaFree(p);
     cudaFree(s->d_counter), cudaFree(s->d_stats);
     for (auto e : s->events) cudaEventDestroy(e);
@@ -802,12 +805,29 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     CU(cudaMalloc(&s->d_images, std::max<size_t>(1, imgs.size()) * sizeof(DevImage)));
     if (!imgs.empty())
         CU(cudaMemcpyAsync(s->d_images, imgs.data(), imgs.size() * sizeof(DevImage), cudaMemcpyHostToDevice, s->stream));
+    // Perlin tables (materials.go:195-200) as F4 gradients + the three permutations
+    {
+        std::vector<DevPerlin> pt(desc->n_perlins);
+        for (uint32_t i = 0; i < desc->n_perlins; i++) {
+            for (int k = 0; k < 256; k++) {
+                pt[i].vec[k].x = desc->perlins[i].vec[k][0], pt[i].vec[k].y = desc->perlins[i].vec[k][1];
+                pt[i].vec[k].z = desc->perlins[i].vec[k][2], pt[i].vec[k].w = 0;
+            }
+            memcpy(pt[i].perm_x, desc->perlins[i].perm_x, 256), memcpy(pt[i].perm_y, desc->perlins[i].perm_y, 256);
+            memcpy(pt[i].perm_z, desc->perlins[i].perm_z, 256);
+        }
+        CU(cudaMalloc(&s->d_perlins, std::max<size_t>(1, pt.size()) * sizeof(DevPerlin)));
+        if (!pt.empty()) {
+            CU(cudaMemcpyAsync(s->d_perlins, pt.data(), pt.size() * sizeof(DevPerlin), cudaMemcpyHostToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream)); // pt is a local
+        }
+    }
     CU(cudaMalloc(&s->d_counter, sizeof(unsigned int)));
     CU(cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long)));
     CU(cudaStreamSynchronize(s->stream));
 
     s->dev.nodes = s->d_nodes, s->dev.sph = s->d_sph, s->dev.meta = s->d_meta, s->dev.mats = s->d_mats;
-    s->dev.images = s->d_images;
+    s->dev.tex.images = s->d_images, s->dev.tex.perlins = s->d_perlins;
     s->dev.quads = s->d_quads, s->dev.n_quad_slots = (uint32_t)n_qslots;
     s->dev.root_ref = s->bvh.root_ref;
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;

@@ -33,6 +33,18 @@ struct DevImage {
     int32_t w, h;
 };
 
+// Perlin's tables on the device (materials.go:195-200): gradients as F4, the three permutations.
+struct DevPerlin {
+    F4 vec[256];
+    uint8_t perm_x[256], perm_y[256], perm_z[256];
+};
+
+// What Texture.GetTexture may have to read besides the material record.
+struct DevTex {
+    const DevImage *images;
+    const DevPerlin *perlins;
+};
+
 struct DevCamera {
     V3 center, pixel00, du, dv, disk_u, disk_v, background;
     int32_t width, height, max_depth;
@@ -138,8 +150,58 @@ RT_HD V3 image_texture(const DevImage &im, V3 oob, float u, float v) {
     return v3((float)r * col_scale, (float)g * col_scale, (float)b * col_scale);
 }
 
+// math.go:58-60, 78-92: Lerp, BiLinearLerp, TriLinearLerp
+RT_HD float lerp1(float t, float x, float y) { return x * (1 - t) + y * t; }
+RT_HD float bilerp(float tx, float ty, float c00, float c10, float c01, float c11) {
+    const float a = lerp1(tx, c00, c10);
+    const float b = lerp1(tx, c01, c11);
+    return lerp1(ty, a, b);
+}
+// materials.go:218-220
+RT_HD float smoothstep(float t) { return t * t * (3 - 2 * t); }
+// Perlin.Noise, materials.go:223-249
+RT_HD float perlin_noise(const DevPerlin &per, V3 p) {
+    const float xi = floorf(p.x), yi = floorf(p.y), zi = floorf(p.z);
+    const float tx = p.x - xi, ty = p.y - yi, tz = p.z - zi;
+    const int rx0 = (int)((long long)xi & 255), rx1 = (rx0 + 1) & 255;
+    const int ry0 = (int)((long long)yi & 255), ry1 = (ry0 + 1) & 255;
+    const int rz0 = (int)((long long)zi & 255), rz1 = (rz0 + 1) & 255;
+    const uint32_t x0 = per.perm_x[rx0], x1 = per.perm_x[rx1], y0 = per.perm_y[ry0], y1 = per.perm_y[ry1];
+    const uint32_t z0 = per.perm_z[rz0], z1 = per.perm_z[rz1];
+#define RT_GRAD(ix, iy, iz, ax, ay, az) dot(v3(per.vec[ix ^ iy ^ iz].x, per.vec[ix ^ iy ^ iz].y, per.vec[ix ^ iy ^ iz].z), v3(ax, ay, az))
+    const float c000 = RT_GRAD(x0, y0, z0, tx, ty, tz);
+    const float c001 = RT_GRAD(x0, y0, z1, tx, ty, tz - 1);
+    const float c010 = RT_GRAD(x0, y1, z0, tx, ty - 1, tz);
+    const float c011 = RT_GRAD(x0, y1, z1, tx, ty - 1, tz - 1);
+    const float c100 = RT_GRAD(x1, y0, z0, tx - 1, ty, tz);
+    const float c101 = RT_GRAD(x1, y0, z1, tx - 1, ty, tz - 1);
+    const float c110 = RT_GRAD(x1, y1, z0, tx - 1, ty - 1, tz);
+    const float c111 = RT_GRAD(x1, y1, z1, tx - 1, ty - 1, tz - 1);
+#undef RT_GRAD
+    const float sx = smoothstep(tx), sy = smoothstep(ty), sz = smoothstep(tz);
+    const float e = bilerp(sx, sy, c000, c100, c010, c110);
+    const float f = bilerp(sx, sy, c001, c101, c011, c111);
+    return lerp1(sz, e, f);
+}
+// Perlin.Turb, materials.go:251-262
+RT_HD float perlin_turb(const DevPerlin &per, V3 p, int depth) {
+    float sum = 0, weight = 1.0f;
+    for (int i = 0; i < depth; i++) {
+        sum += weight * perlin_noise(per, p);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(sum);
+}
+// NoiseTexture.GetTexture, materials.go:285-288 (sin in f64 as math.Sin)
+RT_HD V3 noise_texture(const DevPerlin &per, float scale, V3 point) {
+    point = point * scale;
+    const float s = 0.5f * (1 + (float)sin((double)(point.z + 10 * perlin_turb(per, point, 7))));
+    return v3(1, 1, 1) * s;
+}
+
 // Texture.GetTexture for the texture folded into material record (m0, m1).
-RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, const DevImage *images, const HitInfo &hi) {
+RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, DevTex tex_, const HitInfo &hi) {
     const V3 point = hi.point;
     const uint32_t tex = RT_CODE_TEX(code);
     if (tex == RT_TEX_CHECKER) { // materials.go:127-137
@@ -150,10 +212,11 @@ RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, const DevImage
         if (((x + y + z) & 1) == 0) return v3(m0.x, m0.y, m0.z);
         return v3(m1.x, m1.y, m1.z);
     }
+    if (tex == RT_TEX_NOISE) return noise_texture(tex_.perlins[RT_CODE_IMG(code)], m0.w, point);
     if (tex == RT_TEX_IMAGE) {
         float u = hi.u, v = hi.v;
         if (!hi.is_quad) sphere_uv(hi.front ? hi.normal : hi.normal * -1.0f, u, v); // the outward normal
-        return image_texture(images[RT_CODE_IMG(code)], v3(m0.x, m0.y, m0.z), u, v);
+        return image_texture(tex_.images[RT_CODE_IMG(code)], v3(m0.x, m0.y, m0.z), u, v);
     }
     return v3(m0.x, m0.y, m0.z); // materials.go:155-157
 }
@@ -172,7 +235,7 @@ RT_HD float reflectance(float cos_theta, float eta) {
 // is always written.  On scatter, (o, d) become the scattered ray and `atten` its attenuation.
 // The work shared by several materials (the unit-sphere sample of Lambertian and Metal, Unit(dir)
 // of Metal and Dielectric) is hoisted so that lanes with different materials run it together.
-RT_HD bool shade_surface(const F4 &m0, const F4 &m1, const DevImage *images, const HitInfo &hi,
+RT_HD bool shade_surface(const F4 &m0, const F4 &m1, DevTex tex, const HitInfo &hi,
                          PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
     const uint32_t code = as_uint(m1.w);
     const uint32_t kind = RT_CODE_MAT(code);
@@ -183,7 +246,7 @@ RT_HD bool shade_surface(const F4 &m0, const F4 &m1, const DevImage *images, con
     if (kind == RT_MAT_LAMBERTIAN) { // materials.go:33-42
         V3 dir = hi.normal + ru;
         if (near_zero(dir)) dir = hi.normal;
-        atten = texture_value(m0, m1, code, images, hi);
+        atten = texture_value(m0, m1, code, tex, hi);
         o = hi.point, d = dir;
         return true;
     }
@@ -214,24 +277,24 @@ RT_HD bool shade_surface(const F4 &m0, const F4 &m1, const DevImage *images, con
         return true;
     }
     // DiffuseLight: emits its texture, never scatters (materials.go:301-313)
-    emitted = texture_value(m0, m1, code, images, hi);
+    emitted = texture_value(m0, m1, code, tex, hi);
     return false;
 }
 
 // Sphere hit (hittables.go:118-128) then Emit + Scatter.
-RT_HD bool shade_hit(const F4 &m0, const F4 &m1, const DevImage *images, const F4 &sphere, float t,
+RT_HD bool shade_hit(const F4 &m0, const F4 &m1, DevTex tex, const F4 &sphere, float t,
                      PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
     HitInfo hi;
     complete_hit(sphere, o, d, t, hi);
-    return shade_surface(m0, m1, images, hi, rng, o, d, atten, emitted);
+    return shade_surface(m0, m1, tex, hi, rng, o, d, atten, emitted);
 }
 
 // Quad hit (hittables.go:180-190) then Emit + Scatter.
-RT_HD bool shade_hit_quad(const F4 &m0, const F4 &m1, const DevImage *images, const F4 *__restrict__ quad, float t,
+RT_HD bool shade_hit_quad(const F4 &m0, const F4 &m1, DevTex tex, const F4 *__restrict__ quad, float t,
                           PathRng &rng, V3 &o, V3 &d, V3 &atten, V3 &emitted) {
     HitInfo hi;
     complete_hit_quad(quad, o, d, t, hi);
-    return shade_surface(m0, m1, images, hi, rng, o, d, atten, emitted);
+    return shade_surface(m0, m1, tex, hi, rng, o, d, atten, emitted);
 }
 
 // camera.go:261 (sum * (1/spp)), vec3.go:162-166 (sqrt), 145-152 (clamp, *255.999), 141-143 (int())

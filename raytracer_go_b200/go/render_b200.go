@@ -52,6 +52,7 @@ type b200Flat struct {
 	materials []C.rt_material
 	textures  []C.rt_texture
 	images    []image.Image
+	perlins   []C.rt_perlin
 	matIndex  map[Material]uint32
 	texIndex  map[Texture]uint32
 	seen      map[Hittable]bool
@@ -90,6 +91,19 @@ func (f *b200Flat) texture(t Texture) (uint32, error) {
 		s := float32(1.0 / 65535.0)
 		rec.oob = [3]C.float{C.float(float32(r) * s), C.float(float32(g) * s), C.float(float32(bl) * s)}
 		f.images = append(f.images, tt.img)
+	case *NoiseTexture: // materials.go:280-283: copy Perlin's tables so the device evaluates the same field
+		rec.kind = C.RT_TEX_NOISE
+		rec.scale = C.float(tt.scale)
+		rec.image = C.uint32_t(len(f.perlins))
+		var pt C.rt_perlin
+		for k := 0; k < 256; k++ {
+			v := tt.perlin.randVec3[k]
+			pt.vec[k] = [3]C.float{C.float(v.X), C.float(v.Y), C.float(v.Z)}
+			pt.perm_x[k] = C.uint8_t(tt.perlin.permX[k])
+			pt.perm_y[k] = C.uint8_t(tt.perlin.permY[k])
+			pt.perm_z[k] = C.uint8_t(tt.perlin.permZ[k])
+		}
+		f.perlins = append(f.perlins, pt)
 	default:
 		return 0, fmt.Errorf("b200: texture %T is outside the accelerated path", t)
 	}
@@ -253,6 +267,8 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 	frees = append(frees, fr)
 	pqi, fr := cArray(f.quadIDs)
 	frees = append(frees, fr)
+	ppl, fr := cArray(f.perlins)
+	frees = append(frees, fr)
 
 	desc := C.rt_scene_desc{
 		abi_version: C.RT_B200_ABI_VERSION,
@@ -262,6 +278,7 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 		images: (*C.rt_image)(pi), n_images: C.uint32_t(len(cimgs)),
 		quads: (*C.rt_quad)(pq), n_quads: C.uint64_t(len(f.quads)),
 		sphere_ids: (*C.uint32_t)(psi), quad_ids: (*C.uint32_t)(pqi),
+		perlins: (*C.rt_perlin)(ppl), n_perlins: C.uint32_t(len(f.perlins)),
 	}
 	var scene *C.rt_scene
 	if rc := C.rt_scene_create(&desc, C.int(o.Device), &scene); rc != C.RT_OK {

@@ -14,6 +14,7 @@
 #ifndef RTGO_HPP
 #define RTGO_HPP
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <functional>
@@ -49,7 +50,32 @@ struct ImageTexture : Texture {
     std::vector<uint16_t> rgb16; // img.At(i,j).RGBA() r,g,b, row-major
     Vec3 oob{0, 34678.0f * (float)(1.0 / 65535.0), 0}; // zero colour of *image.YCbCr (JPEG)
 };
+// materials.go:280-295 with Perlin's tables (materials.go:195-216); the reference fills them from a
+// clock-seeded *rand.Rand (main.go:120-123), here from a seed.
+struct NoiseTexture : Texture {
+    rt_perlin perlin;
+    float scale;
+};
 using TexturePtr = std::shared_ptr<Texture>;
+inline TexturePtr NewNoiseTexture(uint64_t seed, float scale) {
+    auto t = std::make_shared<NoiseTexture>();
+    t->scale = scale;
+    uint64_t st = seed;
+    auto next = [&st]() {
+        uint64_t z = (st += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    for (int k = 0; k < 256; k++) // NewVec3RandRange32(-1, 1), materials.go:206
+        for (int c = 0; c < 3; c++) t->perlin.vec[k][c] = -1.0f + (float)(next() >> 40) * (1.0f / 16777216.0f) * 2.0f;
+    uint8_t *perms[3] = {t->perlin.perm_x, t->perlin.perm_y, t->perlin.perm_z};
+    for (auto p : perms) { // Permute(GetNums(256)), materials.go:264-278: target := rand.Intn(i)
+        for (int i = 0; i < 256; i++) p[i] = (uint8_t)i;
+        for (int i = 255; i > 0; i--) std::swap(p[i], p[next() % (uint64_t)i]);
+    }
+    return t;
+}
 inline TexturePtr NewSolidColor(float x, float y, float z) {
     auto t = std::make_shared<SolidColor>();
     t->albedo = NewVec3(x, y, z);
@@ -176,6 +202,7 @@ struct Camera {
         std::vector<rt_material> materials;
         std::vector<rt_texture> textures;
         std::vector<rt_image> images;
+        std::vector<rt_perlin> perlins;
         std::map<const Material *, uint32_t> mat_index;
         std::map<const Texture *, uint32_t> tex_index;
         auto tex_id = [&](const TexturePtr &t, uint32_t *out) -> bool {
@@ -192,6 +219,9 @@ struct Camera {
                 r.kind = RT_TEX_IMAGE, r.image = (uint32_t)images.size();
                 r.oob[0] = im->oob.X, r.oob[1] = im->oob.Y, r.oob[2] = im->oob.Z;
                 images.push_back(rt_image{im->w, im->h, im->rgb16.data()});
+            } else if (auto nt = dynamic_cast<const NoiseTexture *>(t.get())) {
+                r.kind = RT_TEX_NOISE, r.scale = nt->scale, r.image = (uint32_t)perlins.size();
+                perlins.push_back(nt->perlin);
             } else {
                 return false;
             }
@@ -238,6 +268,7 @@ struct Camera {
         desc.materials = materials.data(), desc.n_materials = (uint32_t)materials.size();
         desc.textures = textures.data(), desc.n_textures = (uint32_t)textures.size();
         desc.images = images.data(), desc.n_images = (uint32_t)images.size();
+        desc.perlins = perlins.data(), desc.n_perlins = (uint32_t)perlins.size();
         desc.quads = quads.data(), desc.n_quads = quads.size();
         desc.sphere_ids = sphere_ids.data(), desc.quad_ids = quad_ids.data();
         rt_scene *scene = nullptr;

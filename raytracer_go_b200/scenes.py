@@ -27,7 +27,10 @@ TEXTURE_DT = np.dtype([("kind", np.uint32), ("a", F, 3), ("b", F, 3), ("scale", 
 assert SPHERE_DT.itemsize == C.sizeof(abi.rt_sphere)
 assert MATERIAL_DT.itemsize == C.sizeof(abi.rt_material)
 assert TEXTURE_DT.itemsize == C.sizeof(abi.rt_texture)
+PERLIN_DT = np.dtype([("vec", F, (256, 3)), ("perm_x", np.uint8, 256), ("perm_y", np.uint8, 256),
+                      ("perm_z", np.uint8, 256)])
 assert QUAD_DT.itemsize == C.sizeof(abi.rt_quad)
+assert PERLIN_DT.itemsize == C.sizeof(abi.rt_perlin)
 
 SCENE_SEED_RANDOM = 0x5EED0001
 TEXTURE_SEED_EARTH = 0x5EED0003
@@ -39,12 +42,13 @@ class SceneData:
     """Flat, pointer-free scene (what the Go bridge would fill by walking World.hittables)."""
 
     def __init__(self, spheres, materials, textures, images=(), ray_origin_radius=0.0, name="", quads=None,
-                 sphere_ids=None, quad_ids=None):
+                 sphere_ids=None, quad_ids=None, perlins=None):
         self.spheres = np.ascontiguousarray(spheres, dtype=SPHERE_DT)
         self.quads = np.ascontiguousarray(quads if quads is not None else np.zeros(0, QUAD_DT), dtype=QUAD_DT)
         # object IDs = position in World.hittables (hittables.go:48-53); None = spheres first, then quads
         self.sphere_ids = None if sphere_ids is None else np.ascontiguousarray(sphere_ids, np.uint32)
         self.quad_ids = None if quad_ids is None else np.ascontiguousarray(quad_ids, np.uint32)
+        self.perlins = np.ascontiguousarray(perlins if perlins is not None else np.zeros(0, PERLIN_DT), dtype=PERLIN_DT)
         self.materials = np.ascontiguousarray(materials, dtype=MATERIAL_DT)
         self.textures = np.ascontiguousarray(textures, dtype=TEXTURE_DT)
         self.images = [np.ascontiguousarray(im, dtype=np.uint16) for im in images]  # (h, w, 3)
@@ -68,6 +72,8 @@ class SceneData:
         d.images = imgs
         d.n_images = len(self.images)
         d.ray_origin_radius = self.ray_origin_radius
+        d.perlins = self.perlins.ctypes.data_as(C.POINTER(abi.rt_perlin))
+        d.n_perlins = len(self.perlins)
         d.quads = self.quads.ctypes.data_as(C.POINTER(abi.rt_quad))
         d.n_quads = len(self.quads)
         if self.sphere_ids is not None or self.quad_ids is not None:
@@ -82,12 +88,12 @@ class SceneData:
         return len(self.spheres) + len(self.quads)
 
     def nbytes(self):
-        return (self.spheres.nbytes + self.quads.nbytes + self.materials.nbytes + self.textures.nbytes
+        return (self.spheres.nbytes + self.quads.nbytes + self.materials.nbytes + self.textures.nbytes + self.perlins.nbytes
                 + sum(im.nbytes for im in self.images))
 
     def sha256(self):
         h = hashlib.sha256()
-        for a in (self.spheres, self.quads, self.materials, self.textures, *self.images):
+        for a in (self.spheres, self.quads, self.materials, self.textures, self.perlins, *self.images):
             h.update(a.tobytes())
         return h.hexdigest()
 
@@ -130,6 +136,53 @@ def box_quads(a, b, material):
         _quad((mn[0], mx[1], mx[2]), dx, neg(dz), material),
         _quad((mn[0], mn[1], mn[2]), dx, dz, material),
     ]
+
+
+def new_perlin(seed):
+    """NewPerlin (materials.go:202-216): 256 vectors NewVec3RandRange32(-1, 1) and three permutations
+    made by Permute (materials.go:272-278: `target := rand.Intn(i)`, i from 255 down to 1).  The
+    reference draws them from clock-seeded generators; here from a seeded numpy Philox."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    p = np.zeros((), PERLIN_DT)
+    r = rng.random((256, 3), dtype=np.float32)
+    p["vec"] = F(-1) + r * F(2)
+    for name in ("perm_x", "perm_y", "perm_z"):
+        a = np.arange(256, dtype=np.uint8)
+        for i in range(255, 0, -1):
+            t = int(rng.integers(0, i))
+            a[i], a[t] = a[t], a[i]
+        p[name] = a
+    return p
+
+
+def perlin_demo_scene(seed=0x5EED0002):
+    """main.go:106-130: two spheres with the marble NoiseTexture(scale 4)."""
+    tex = [_tex(abi.RT_TEX_NOISE, scale=4.0, image=0)]
+    mats = [_mat(abi.RT_MAT_LAMBERTIAN, texture=0)]
+    sph = [_sph((0, -1000, 0), 1000, 0), _sph((0, 2, 0), 2, 0)]
+    return SceneData(np.array(sph, SPHERE_DT), np.array(mats, MATERIAL_DT), np.array(tex, TEXTURE_DT),
+                     perlins=np.array([new_perlin(seed)], PERLIN_DT), name="perlin")
+
+
+def simple_light_scene(seed=0x5EED0002):
+    """main.go:162-192: marble ground and sphere, a red sphere, and a spherical DiffuseLight(4,4,4)."""
+    tex = [_tex(abi.RT_TEX_NOISE, scale=4.0, image=0), _tex(a=(1, 0, 0)), _tex(a=(4, 4, 4))]
+    mats = [_mat(abi.RT_MAT_LAMBERTIAN, texture=0), _mat(abi.RT_MAT_LAMBERTIAN, texture=1),
+            _mat(abi.RT_MAT_DIFFUSE_LIGHT, texture=2)]
+    sph = [_sph((0, -1000, 0), 1000, 0), _sph((0, 2, 0), 2, 0), _sph((-4, 2, 4), 2, 1), _sph((0, 7, 0), 2, 2)]
+    return SceneData(np.array(sph, SPHERE_DT), np.array(mats, MATERIAL_DT), np.array(tex, TEXTURE_DT),
+                     perlins=np.array([new_perlin(seed)], PERLIN_DT), name="simple-light")
+
+
+def simple_light_camera_options(width=400, spp=500):
+    """main.go:163-173."""
+    return camera_options(width, spp, look_from=(26, 3, 6), look_at=(0, 2, 0), vfov_deg=20.0, defocus_deg=0.0,
+                          background=(0, 0, 0))
+
+
+def perlin_camera_options(width=400, spp=100):
+    """main.go:107-117."""
+    return camera_options(width, spp, look_from=(13, 2, 3), look_at=(0, 0, 0), vfov_deg=20.0, defocus_deg=0.0)
 
 
 def cornell_box_scene():

@@ -18,6 +18,8 @@ struct HostScene {
     std::vector<F4> mats;
     std::vector<DevImage> images;
     std::vector<std::vector<uint16_t>> texels;
+    std::vector<DevPerlin> perlins;
+    DevTex tex() const { return DevTex{images.data(), perlins.data()}; }
 };
 
 void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *s) {
@@ -37,16 +39,25 @@ void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *
             for (int c = 0; c < 3; c++) s->texels[i][4 * k + c] = im.rgb16[3 * k + c];
         s->images[i].texels = s->texels[i].data(), s->images[i].w = im.w, s->images[i].h = im.h;
     }
+    s->perlins.resize(d->n_perlins);
+    for (uint32_t i = 0; i < d->n_perlins; i++) {
+        for (int k = 0; k < 256; k++) {
+            s->perlins[i].vec[k].x = d->perlins[i].vec[k][0], s->perlins[i].vec[k].y = d->perlins[i].vec[k][1];
+            s->perlins[i].vec[k].z = d->perlins[i].vec[k][2], s->perlins[i].vec[k].w = 0;
+        }
+        memcpy(s->perlins[i].perm_x, d->perlins[i].perm_x, 256), memcpy(s->perlins[i].perm_y, d->perlins[i].perm_y, 256);
+        memcpy(s->perlins[i].perm_z, d->perlins[i].perm_z, 256);
+    }
 }
 // Emit + Scatter at a HitRec (sphere or quad slot), like the kernel does.
 bool shade_at(const HostScene &s, const HitRec &h, PathRng &rng, V3 &o, V3 &dir, V3 &atten, V3 &emitted) {
     if (h.slot & RT_HIT_QUAD) {
         const F4 *q = s.bvh.quad.data() + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
         const uint32_t mi = as_uint(q[1].w);
-        return shade_hit_quad(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), q, h.t, rng, o, dir, atten, emitted);
+        return shade_hit_quad(s.mats[2 * mi], s.mats[2 * mi + 1], s.tex(), q, h.t, rng, o, dir, atten, emitted);
     }
     const int mi = s.bvh.meta[h.slot].y;
-    return shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[h.slot], h.t, rng, o, dir, atten, emitted);
+    return shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.tex(), s.bvh.sph[h.slot], h.t, rng, o, dir, atten, emitted);
 }
 } // namespace
 
@@ -166,7 +177,7 @@ extern "C" int64_t hs_segment_stats(const rt_scene_desc *d, const rt_camera *cam
                 if (h.slot == RT_REF_NONE) break;
                 const int mi = s.bvh.meta[h.slot].y;
                 V3 atten, emitted;
-                if (!shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[h.slot], h.t, rng, o, dir, atten, emitted)) break;
+                if (!shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.tex(), s.bvh.sph[h.slot], h.t, rng, o, dir, atten, emitted)) break;
                 depth++;
             }
         }
@@ -235,7 +246,7 @@ extern "C" int64_t hs_traversal_events(const rt_scene_desc *d, const rt_camera *
                 if (best == RT_REF_NONE) break;
                 const int mi = s.bvh.meta[best].y;
                 V3 atten, emitted;
-                if (!shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.images.data(), s.bvh.sph[best], tbest, rng, o, dir, atten, emitted)) break;
+                if (!shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.tex(), s.bvh.sph[best], tbest, rng, o, dir, atten, emitted)) break;
                 depth++;
             }
         }

@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(rtlib):
 
 def test_struct_layouts_match_the_header():
     """Compile a probe against the real header and compare sizeof/offsetof with ctypes."""
-    structs = {n: getattr(abi, n) for n in ("rt_sphere", "rt_quad", "rt_material", "rt_texture", "rt_image", "rt_scene_desc",
+    structs = {n: getattr(abi, n) for n in ("rt_sphere", "rt_quad", "rt_material", "rt_texture", "rt_image", "rt_perlin", "rt_scene_desc",
                                            "rt_camera", "rt_camera_options", "rt_render_opts", "rt_stats",
                                            "rt_bvh_info")}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]

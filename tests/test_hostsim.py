@@ -176,3 +176,18 @@ def test_quad_edge_cases(hs, orc):
     rids, rts = orc.trace(s, o, d)
     assert np.array_equal(ids, rids) and ids.tolist() == [0, 0, -1, -1, -1, 0]
     assert ts[0] == 2.0 and ts[1] == 1.0 and np.array_equal(ts[rids >= 0], rts[rids >= 0])
+
+
+@pytest.mark.parametrize("name", ["perlin", "simple-light"])
+def test_noise_texture_scenes_equal_oracle(hs, orc, name):
+    """Perlin / NoiseTexture (materials.go:195-295; main.go:106-130, 162-192)."""
+    if name == "perlin":
+        s, o = scenes.perlin_demo_scene(), scenes.perlin_camera_options(96, 4)
+    else:
+        s, o = scenes.simple_light_scene(), scenes.simple_light_camera_options(96, 8)
+    cam = orc.camera_from_options(o)
+    rgb, acc = _hs_render(hs, s, cam, 21, cam.spp)
+    rrgb, racc, _ = orc.render(s, cam, 21, order=orc.ORDER_ITERATIVE)
+    assert np.array_equal(acc.view(np.uint32), racc.view(np.uint32))
+    assert np.array_equal(rgb, rrgb)
+    assert len(np.unique(rgb.reshape(-1, 3), axis=0)) > 50   # marble, not a flat colour

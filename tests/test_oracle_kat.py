@@ -315,3 +315,20 @@ def test_cornell_box_renders(orc):
     assert left[1] > left[0] and right[0] > right[1]            # green wall at image-left, red at image-right
     r2, a2, _ = orc.render(s, cam, 3, mode=orc.MODE_REF_BVH)
     assert (np.abs(a2 - acc) > 1e-3).any(-1).mean() < 0.01
+
+
+def test_perlin_noise_kat(orc):
+    """materials.go:223-288: at lattice points every corner weight's offset vector is 0, so Noise and
+    Turb vanish and the marble is 0.5*(1 + sin(scale*z)); off-lattice the value stays in [0, 1]."""
+    s = scenes.perlin_demo_scene()
+    v = orc.texture(s, 0, 0, 0, (1, 2, 0.75))            # scale 4 -> (4, 8, 3): all octaves on the lattice
+    want = np.float32(0.5) * (np.float32(1) + np.float32(math.sin(3.0)))
+    assert v.tolist() == [float(want)] * 3
+    rng = np.random.default_rng(0)
+    vals = np.array([orc.texture(s, 0, 0, 0, p)[0] for p in rng.uniform(-5, 5, size=(300, 3))])
+    assert vals.min() >= 0 and vals.max() <= 1 and vals.std() > 0.2
+    # negative coordinates index the tables through `& 255` (Go ints are two's complement)
+    assert 0 <= orc.texture(s, 0, 0, 0, (-0.3, -7.2, -100.6))[0] <= 1
+    # a different table seed gives a different field
+    s2 = scenes.perlin_demo_scene(seed=99)
+    assert orc.texture(s2, 0, 0, 0, (0.3, 0.4, 0.5))[0] != orc.texture(s, 0, 0, 0, (0.3, 0.4, 0.5))[0]
