@@ -307,7 +307,13 @@ def main():
     smem_bw = bytes_per_ray * (rays / world / args.steps) / (mk_ms / args.steps * 1e-3) / 1e9
     roofline = {
         "bound": "fp32_issue", "kernel": "render_kernel", "achieved": achieved, "peak": peak_instr,
-        "unit": "T lane-instr/s", "frac": achieved / peak_instr, "traffic": None,
+        "unit": "T lane-instr/s", "frac": achieved / peak_instr,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one render_kernel launch of 31.59 M paths (39 spp x
+        # 810 000 px, the C2 pass size), ncu --set full, profiles/r01i_render_kernel_ncu_full.txt; the
+        # algorithmic figure is the 16-byte radiance record each path writes
+        "traffic": {"dram_bytes_per_launch": 452.7e6, "algorithmic_bytes_per_launch": 16 * 31.59e6,
+                    "source": "profiles/r01i_render_kernel_ncu_full.txt (C2 pass: 39 spp x 1200x675)"}
+        if args.config == "C2" and not args.width else None,
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz {peaks['sm_max_mhz']:.0f} ({peak_src} MEASURED_PEAKS.json clock)",
         "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": n_box,
         "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit, "counted_at_spp": cnt_spp,
