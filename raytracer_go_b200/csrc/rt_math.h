@@ -52,10 +52,18 @@ RT_HD float div32(float x, float y) {
     return x / y;
 #endif
 }
+// 1 / x, IEEE round-to-nearest (bit-identical to 1.0f / x; cheaper than a general divide on the GPU)
+RT_HD float rcp32(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
 // vec3.go:103-107: Scale(1/len)
 RT_HD V3 unit(V3 a) {
     float l = sqrt32(lensq(a));
-    return a * div32(1.0f, l);
+    return a * rcp32(l);
 }
 // vec3.go:212-214
 RT_HD V3 reflect(V3 v, V3 n) { return v - n * (2 * dot(v, n)); }

@@ -255,3 +255,73 @@ out:
     *n_rays_out = rays;
     return n;
 }
+
+// As hs_traversal_events, but also records each ray's origin and direction (6 floats per ray) so
+// that ray-sorting policies can be evaluated offline.
+extern "C" int64_t hs_traversal_events_rays(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32_t spp,
+                                            int64_t pixel_begin, int64_t n_pixels, int max_leaf, int8_t *tokens,
+                                            int64_t max_tokens, float *rays_out, int64_t max_rays, int64_t *n_rays_out) {
+    HostScene s;
+    load(d, max_leaf, 0, &s);
+    DevCamera c = make_dev_camera(*cam);
+    int64_t n = 0, rays = 0;
+    const F4 *nodes = s.bvh.nodes.data();
+    for (int64_t pp = 0; pp < n_pixels; pp++) {
+        int64_t pix = pixel_begin + pp;
+        for (int k = 0; k < spp; k++) {
+            PathRng rng;
+            rng.init(seed, (uint32_t)pix, (uint32_t)k);
+            V3 o, dir;
+            generate_ray(c, rng, (int)(pix % cam->width), (int)(pix / cam->width), o, dir);
+            for (int depth = 0; depth < c.max_depth;) {
+                if (n + 130 > max_tokens || rays >= max_rays) goto out;
+                float *ro = rays_out + 7 * rays;
+                ro[0] = o.x, ro[1] = o.y, ro[2] = o.z, ro[3] = dir.x, ro[4] = dir.y, ro[5] = dir.z, ro[6] = (float)depth;
+                const V3 inv = v3(cull_rcp(dir.x), cull_rcp(dir.y), cull_rcp(dir.z));
+                const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+                const float a = lensq(dir);
+                float tbest = INFINITY;
+                uint32_t best = RT_REF_NONE, ref = s.bvh.root_ref;
+                LocalStack<64> stack;
+                stack.reset();
+                for (;;) {
+                    int run = 0;
+                    while (!(ref & RT_LEAF)) {
+                        const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1], r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
+                        float tl, tr;
+                        const bool hl = box_test(l0, l1, inv, noi, 0.001f, tbest, tl), hr = box_test(r0, r1, inv, noi, 0.001f, tbest, tr);
+                        const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
+                        if (hl && hr) {
+                            const bool lf = tl <= tr;
+                            stack.push(lf ? rref : lref);
+                            ref = lf ? lref : rref;
+                        } else if (hl) ref = lref;
+                        else if (hr) ref = rref;
+                        else ref = stack.pop();
+                        if (++run == 127) tokens[n++] = 127, run = 0;
+                    }
+                    if (run) tokens[n++] = (int8_t)run;
+                    if (ref == RT_REF_NONE) break;
+                    const uint32_t first = (ref & RT_LEAF_SLOT_MASK) >> 3, count = (ref & 7u) + 1;
+                    for (uint32_t q = first; q < first + count; q++) {
+                        float t;
+                        if (!sphere_candidate(s.bvh.sph[q], o, dir, a, 0.001f, t)) continue;
+                        if (t < tbest) tbest = t, best = q;
+                    }
+                    tokens[n++] = (int8_t)(-(int)count);
+                    ref = stack.pop();
+                }
+                tokens[n++] = 0;
+                rays++;
+                if (best == RT_REF_NONE) break;
+                const int mi = s.bvh.meta[best].y;
+                V3 atten, emitted;
+                if (!shade_hit(s.mats[2 * mi], s.mats[2 * mi + 1], s.tex(), s.bvh.sph[best], tbest, rng, o, dir, atten, emitted)) break;
+                depth++;
+            }
+        }
+    }
+out:
+    *n_rays_out = rays;
+    return n;
+}
