@@ -219,6 +219,15 @@ int rt_scene_set_stream(rt_scene *scene, void *cuda_stream);
 int rt_render(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts,
               uint8_t *rgb_out, float *accum_out, rt_stats *stats);
 
+/* The same render on several GPUs of the box from ONE call (a single host process such as the Go
+ * program): sample-split.  Device k of `devices` renders its share of the samples on
+ * its own host thread; the FP32 accumulators are peer-copied to devices[0], added in device order
+ * and resolved there.  Takes the scene description (a scene handle lives on one device).  Every
+ * (pixel, sample) keeps its single-GPU Philox stream; only the FP32 summation order differs. */
+int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
+                    const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
+                    rt_stats *stats);
+
 /* Sample-split building blocks: accumulate `opts->sample_count` samples per pixel,
  * global sample indices [sample_offset, sample_offset+sample_count), into a DEVICE buffer of
  * width*height*3 float32 sums (overwritten, not added to).  The caller reduces the buffers of

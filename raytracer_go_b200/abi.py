@@ -106,6 +106,8 @@ PROTOTYPES = {
     "rt_workspace_release": (None, [C.c_int]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_opts),
                             C.c_void_p, C.c_void_p, C.POINTER(rt_stats)]),
+    "rt_render_multi": (C.c_int, [C.POINTER(rt_scene_desc), C.POINTER(rt_camera), C.POINTER(rt_render_opts),
+                                  C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(rt_stats)]),
     "rt_render_accum_device": (C.c_int, [C.c_void_p, C.POINTER(rt_camera),
                                          C.POINTER(rt_render_opts), C.c_void_p,
                                          C.POINTER(rt_stats)]),

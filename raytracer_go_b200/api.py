@@ -96,6 +96,21 @@ class Scene:
         return nodes, ids, info
 
 
+def render_multi(data, cam, devices, seed=scenes.RENDER_SEED, sample_offset=0, sample_count=0, want_accum=False):
+    """rt_render_multi: one call, several GPUs (sample-split inside the library)."""
+    desc, keep = data.to_desc()
+    H, W = cam.height, cam.width
+    rgb = np.empty((H, W, 3), np.uint8)
+    acc = np.empty((H, W, 3), np.float32) if want_accum else None
+    devs = (C.c_int32 * len(devices))(*devices)
+    opts = abi.rt_render_opts(seed, devices[0], sample_offset, sample_count, 0)
+    st = abi.rt_stats()
+    lib.check(lib.load().rt_render_multi(C.byref(desc), C.byref(cam), C.byref(opts), devs, len(devices),
+                                         rgb.ctypes.data_as(C.c_void_p),
+                                         acc.ctypes.data_as(C.c_void_p) if want_accum else None, C.byref(st)))
+    return rgb, acc, st
+
+
 def resolve_device(d_accum_ptr, width, height, total_spp, device=0, cuda_stream=0):
     rgb = np.empty((height, width, 3), np.uint8)
     lib.check(lib.load().rt_resolve_device(C.c_void_p(d_accum_ptr), width, height, total_spp, device,

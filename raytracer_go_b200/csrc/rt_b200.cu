@@ -25,6 +25,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -1138,6 +1139,145 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, scene->events[0], scene->events[1]));
     if (stats) stats->ms_render = ms, stats->ms_total = (float)(now_ms() - t0), stats->kernel_launches = launches;
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one call, several GPUs (what a single host process such as the Go program needs)
+// ---------------------------------------------------------------------------------------------
+__global__ void add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = dst[i] + src[i];
+}
+
+// Sample-split inside the library: device k renders its share of camera->spp into its
+// own FP32 accumulator on its own host thread; the accumulators are peer-copied to devices[0] and
+// added in device order (deterministic), devices[0] resolves.  Every (pixel, sample) keeps the
+// Philox stream it has in a single-GPU render, so only the FP32 summation order differs.
+extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
+                               const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
+                               rt_stats *stats) {
+    if (!desc || !opts || !rgb_out || !devices || n_devices < 1) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_camera(camera);
+    if (rc != RT_OK) return rc;
+    const double t0 = now_ms();
+    const int spp = opts->sample_count > 0 ? opts->sample_count : camera->spp;
+    if (spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "sample count %d < 1", spp);
+    std::vector<int> devs(devices, devices + n_devices);
+    {
+        std::vector<int> sorted = devs;
+        std::sort(sorted.begin(), sorted.end());
+        if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end())
+            return fail(RT_ERR_INVALID_ARGUMENT, "duplicate device in the device list");
+        for (int d : sorted)
+            if (d < 0 || d >= RT_MAX_DEVICES) return fail(RT_ERR_INVALID_ARGUMENT, "device %d out of range", d);
+    }
+    const size_t n_acc = (size_t)camera->width * camera->height * 3;
+    const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)camera->height;
+
+    // workspaces are locked in ascending device order (no lock-order inversion between calls)
+    std::vector<int> order = devs;
+    std::sort(order.begin(), order.end());
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int d : order) locks.emplace_back(g_ws[d].mu);
+
+    struct Job {
+        rt_scene *scene = nullptr;
+        rt_render_opts o;
+        rt_stats st;
+        int rc = RT_OK;
+        std::string err;
+    };
+    std::vector<Job> jobs(n_devices);
+    const int base = spp / n_devices, rem = spp % n_devices;
+    std::vector<std::thread> threads;
+    for (int k = 0; k < n_devices; k++) {
+        Job &j = jobs[k];
+        j.o = *opts;
+        j.o.device = devs[k];
+        j.o.sample_count = base + (k < rem ? 1 : 0);
+        j.o.sample_offset = opts->sample_offset + k * base + std::min(k, rem);
+        memset(&j.st, 0, sizeof j.st);
+        threads.emplace_back([&, k]() {
+            Job &jj = jobs[k];
+            if (jj.o.sample_count == 0) return; // more devices than samples
+            jj.rc = rt_scene_create(desc, devs[k], &jj.scene);
+            if (jj.rc == RT_OK) {
+                Workspace &ws = g_ws[devs[k]];
+                jj.rc = ws_reserve(ws.accum, ws.accum_cap, n_acc);
+                uint32_t launches = 0;
+                if (jj.rc == RT_OK) jj.rc = scene_events(jj.scene, 2);
+                if (jj.rc == RT_OK) jj.rc = cudaEventRecord(jj.scene->events[0], jj.scene->stream) == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+                if (jj.rc == RT_OK) jj.rc = render_accum(jj.scene, camera, &jj.o, ws.accum, &jj.st, &launches);
+                if (jj.rc == RT_OK) {
+                    cudaEventRecord(jj.scene->events[1], jj.scene->stream);
+                    if (cudaStreamSynchronize(jj.scene->stream) != cudaSuccess) jj.rc = fail(RT_ERR_CUDA, "render failed on device %d", devs[k]);
+                    else cudaEventElapsedTime(&jj.st.ms_render, jj.scene->events[0], jj.scene->events[1]);
+                    jj.st.kernel_launches = launches;
+                }
+            }
+            if (jj.rc != RT_OK) jj.err = rt_last_error(); // thread-local: carry it to the caller's thread
+        });
+    }
+    for (auto &t : threads) t.join();
+    auto cleanup = [&]() {
+        for (auto &j : jobs)
+            if (j.scene) free_scene(j.scene);
+    };
+    for (auto &j : jobs)
+        if (j.rc != RT_OK) {
+            const int code = j.rc;
+            const std::string msg = j.err;
+            cleanup();
+            return fail(code, "%s", msg.c_str());
+        }
+
+    // gather on devices[0]: peer copy + add, in device order
+    const int root = devs[0];
+    Workspace &w0 = g_ws[root];
+    cudaError_t e = cudaSetDevice(root);
+    float *tmp = nullptr;
+    if (e == cudaSuccess && n_devices > 1) e = cudaMalloc(&tmp, n_acc * sizeof(float));
+    cudaStream_t st0 = jobs[0].scene->stream;
+    for (int k = 1; k < n_devices && e == cudaSuccess; k++) {
+        if (jobs[k].o.sample_count == 0) continue;
+        e = cudaMemcpyPeerAsync(tmp, root, g_ws[devs[k]].accum, devs[k], n_acc * sizeof(float), st0);
+        if (e == cudaSuccess) {
+            add_kernel<<<(unsigned)((n_acc + 255) / 256), 256, 0, st0>>>(w0.accum, tmp, n_acc);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) {
+        rc = ws_reserve(w0.rgb, w0.rgb_cap, (size_t)n_pix * 3);
+        if (rc == RT_OK) rc = ws_reserve(w0.h_rgb, w0.h_rgb_cap, (size_t)n_pix * 3, true);
+        if (rc == RT_OK && accum_out) rc = ws_reserve(w0.h_accum, w0.h_accum_cap, n_acc, true);
+        if (rc == RT_OK) {
+            resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st0>>>(w0.accum, w0.rgb, n_pix, 1.0f / (float)spp);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w0.h_rgb, w0.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st0);
+            if (e == cudaSuccess && accum_out) e = cudaMemcpyAsync(w0.h_accum, w0.accum, n_acc * sizeof(float), cudaMemcpyDeviceToHost, st0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+            if (e == cudaSuccess) {
+                memcpy(rgb_out, w0.h_rgb, (size_t)n_pix * 3);
+                if (accum_out) memcpy(accum_out, w0.h_accum, n_acc * sizeof(float));
+            }
+        }
+    }
+    if (tmp) cudaFree(tmp);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (auto &j : jobs) {
+            stats->samples += j.st.samples, stats->rays += j.st.rays, stats->hits += j.st.hits;
+            stats->box_tests += j.st.box_tests, stats->sphere_tests += j.st.sphere_tests;
+            stats->kernel_launches += j.st.kernel_launches, stats->megakernel_launches += j.st.megakernel_launches;
+            stats->ms_render = std::max(stats->ms_render, j.st.ms_render);
+            stats->ms_megakernel = std::max(stats->ms_megakernel, j.st.ms_megakernel);
+        }
+        stats->ms_total = (float)(now_ms() - t0);
+    }
+    cleanup();
+    if (rc != RT_OK) return rc;
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "multi-device gather failed: %s", cudaGetErrorString(e));
     return RT_OK;
 }
 

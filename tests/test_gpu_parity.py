@@ -346,3 +346,29 @@ def test_noise_texture_scenes_match_oracle(gpu, orc, name):
     assert np.allclose(acc, racc, rtol=1e-5, atol=1e-6)
     assert (np.abs(rgb.astype(int) - rrgb.astype(int)) <= 1).all() and (rgb != rrgb).any(-1).mean() < 1e-3
     assert st.rays == rst.rays
+
+
+def test_render_multi_single_device_equals_render(gpu, random_scene):
+    """rt_render_multi on one device is rt_render (same samples, same summation order)."""
+    cam = _cam(200, 6)
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    rgb2, acc2, st2 = api.render_multi(random_scene, cam, [0], SEED, want_accum=True)
+    assert np.array_equal(acc.view(np.uint32), acc2.view(np.uint32)) and np.array_equal(rgb, rgb2)
+    assert st2.samples == st.samples and st2.rays == st.rays
+
+
+def test_render_multi_two_devices(gpu, random_scene):
+    """One call, two GPUs (sample-split inside the library): the same per-sample radiances summed in
+    a different order — equal to rounding, and the samples/rays counts are those of one GPU."""
+    if gpu < 2:
+        pytest.skip("needs two B200s (run with gpurun --gpus 2)")
+    cam = _cam(320, 9)
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    rgb2, acc2, st2 = api.render_multi(random_scene, cam, [0, 1], SEED, want_accum=True)
+    assert st2.samples == st.samples and st2.rays == st.rays and st2.hits == st.hits
+    assert np.allclose(acc2, acc, rtol=2e-6, atol=1e-6)
+    assert (np.abs(rgb2.astype(int) - rgb.astype(int)) <= 1).all()
+    rgb3, acc3, _ = api.render_multi(random_scene, cam, [1, 0], SEED, want_accum=True)
+    assert np.allclose(acc3, acc, rtol=2e-6, atol=1e-6)
