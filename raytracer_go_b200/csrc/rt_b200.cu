@@ -1,16 +1,8 @@
-// rt_b200.cu — CUDA kernels (sm_100a) and the C ABI of librt_b200.so (include/rt_b200.h).
+// rt_b200.cu — the C ABI of librt_b200.so (include/rt_b200.h).
 //
-// Kernels
-//   render_kernel     persistent megakernel: one lane = one (pixel, sample) path at a time
-//                     (camera.go:254-299 + ray.go:32-54 + bvh.go:220-249 + hittables.go:96-132 +
-//                     materials.go), lanes regenerate from a warp-private chunk of the path index
-//                     space when their path ends; the scene (nodes, spheres, materials) is staged
-//                     once per CTA in shared memory when it fits, read with LDS.128.
-//   reduce_kernel     per pixel, adds the pass's per-sample radiances to the FP32 accumulator in
-//                     sample order — exactly the sequential `sample.Add(s)` of camera.go:256-260.
-//   resolve_kernel    camera.go:261 + vec3.go:141-166: 1/spp, sqrt, clamp, *255.999, truncate.
-//   trace_kernel      rt_trace parity hook: closest hit (object index, t) for a ray batch.
-//   primary_kernel    rt_primary_rays parity hook: Camera.GetRay on the device.
+// Host side of the library: error reporting, the per-device workspace, the scene handle (host BVH
+// build, flattening, upload), kernel launches and every extern "C" entry point.  The kernels are in
+// rt_kernels.cuh; the per-ray arithmetic in rt_trace.h / rt_shade.h / rt_rng.h / rt_math.h.
 //
 // Compiled with -fmad=false: see rt_math.h.  No tensor cores (not a contraction), no RT cores
 // (B200 has none).  There is no CPU path: every entry point that computes needs an sm_100 device.
@@ -59,500 +51,7 @@ static int fail(int code, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-// ---------------------------------------------------------------------------------------------
-// device-side scene
-// ---------------------------------------------------------------------------------------------
-struct DevScene {
-    const F4 *nodes;
-    const F4 *sph;
-    const I2 *meta;
-    const F4 *mats;
-    DevTex tex;      // images and Perlin tables (global memory)
-    const F4 *quads; // RT_QUAD_F4 x F4 per quad slot
-    uint32_t root_ref, n_nodes, n_slots, n_mats, n_quad_slots;
-    uint32_t stack_depth; // entries per thread for the shared-memory stack
-};
-
-static size_t scene_smem_bytes(const DevScene &s) {
-    return (size_t)s.n_nodes * 32 + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 +
-           (size_t)s.n_quad_slots * 16 * RT_QUAD_F4 + (size_t)s.n_slots * 8;
-}
-
-#define RT_LOCAL_STACK 64
-
-// Stage the scene arrays in shared memory (LDG.128 -> STS.128), return the carved pointers.
-struct SmemScene {
-    const F4 *nodes, *sph, *mats, *quads;
-    const I2 *meta;
-    uint32_t *stack;
-};
-
-__device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned char *smem) {
-    F4 *nodes = reinterpret_cast<F4 *>(smem);
-    F4 *sph = nodes + 2 * (size_t)sc.n_nodes;
-    F4 *mats = sph + sc.n_slots;
-    F4 *quads = mats + 2 * (size_t)sc.n_mats;
-    I2 *meta = reinterpret_cast<I2 *>(quads + (size_t)RT_QUAD_F4 * sc.n_quad_slots);
-    uint32_t *stack = reinterpret_cast<uint32_t *>(meta + sc.n_slots + (sc.n_slots & 1));
-    const uint4 *src;
-    uint4 *dst;
-    src = reinterpret_cast<const uint4 *>(sc.nodes), dst = reinterpret_cast<uint4 *>(nodes);
-    for (uint32_t i = threadIdx.x; i < 2 * sc.n_nodes; i += blockDim.x) dst[i] = __ldg(src + i);
-    src = reinterpret_cast<const uint4 *>(sc.sph), dst = reinterpret_cast<uint4 *>(sph);
-    for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) dst[i] = __ldg(src + i);
-    src = reinterpret_cast<const uint4 *>(sc.mats), dst = reinterpret_cast<uint4 *>(mats);
-    for (uint32_t i = threadIdx.x; i < 2 * sc.n_mats; i += blockDim.x) dst[i] = __ldg(src + i);
-    src = reinterpret_cast<const uint4 *>(sc.quads), dst = reinterpret_cast<uint4 *>(quads);
-    for (uint32_t i = threadIdx.x; i < RT_QUAD_F4 * sc.n_quad_slots; i += blockDim.x) dst[i] = __ldg(src + i);
-    const uint2 *s2 = reinterpret_cast<const uint2 *>(sc.meta);
-    uint2 *d2 = reinterpret_cast<uint2 *>(meta);
-    for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) d2[i] = __ldg(s2 + i);
-    __syncthreads();
-    SmemScene r;
-    r.nodes = nodes, r.sph = sph, r.mats = mats, r.quads = quads, r.meta = meta, r.stack = stack;
-    return r;
-}
-
-static size_t smem_total_bytes(const DevScene &s, int block) {
-    size_t b = scene_smem_bytes(s) + ((s.n_slots & 1) ? 8 : 0);
-    return b + (size_t)s.stack_depth * block * 4;
-}
-
-// ---------------------------------------------------------------------------------------------
-// render megakernel
-// ---------------------------------------------------------------------------------------------
-struct RenderParams {
-    DevScene sc;
-    DevCamera cam;
-    uint64_t seed;
-    uint32_t pixel_begin;  // first pixel of this pass (row-major index)
-    uint32_t sample_begin; // global index of the first sample of this pass
-    uint32_t spp_pass;     // samples per pixel in this pass
-    uint32_t total_paths;  // n_pixels_pass * spp_pass
-    float4 *samples;       // [total_paths] radiance of path (pixel - pixel_begin) * spp_pass + k
-    unsigned int *counter; // next unclaimed path index
-    unsigned long long *stats; // rays, hits, box tests, sphere tests
-    uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
-};
-
-#define RT_CHUNK 256u /* path indices a warp claims per atomic */
-
-// BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
-template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS>
-__global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_constant__ RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
-    const I2 *meta = p.sc.meta;
-    uint32_t *stack_mem = nullptr;
-    if (SMEM) {
-        SmemScene s = stage_scene(p.sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta, stack_mem = s.stack;
-    }
-    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
-    Stack stack;
-    if constexpr (SMEM) {
-        stack.base = stack_mem + threadIdx.x;
-        stack.stride = BLOCK;
-    }
-
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    uint32_t warp_next = 0, warp_end = 0;
-    bool exhausted = false;
-
-    bool alive = false;
-    uint32_t idx = 0;
-    int depth = 0;
-    V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1), rad = v3(0, 0, 0);
-    PathRng rng;
-    rng.init(0, 0, 0);
-    unsigned long long n_rays = 0, n_hits = 0;
-    WorkCounters wc;
-    wc.box_tests = wc.sphere_tests = 0;
-
-    for (;;) {
-        // ---- regeneration: dead lanes take the next path indices of the warp's chunk ----
-        const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-        if (dead == 0xffffffffu || (uint32_t)__popc(dead) >= p.regen_min) {
-            if (warp_next >= warp_end && !exhausted) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= p.total_paths) {
-                    exhausted = true;
-                } else {
-                    warp_next = base;
-                    warp_end = min(base + RT_CHUNK, p.total_paths);
-                }
-            }
-            const uint32_t avail = warp_end - warp_next;
-            const uint32_t rank = __popc(dead & lt_mask);
-            if (!alive && rank < avail) {
-                idx = warp_next + rank;
-                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-                const uint32_t pixel = p.pixel_begin + pp;
-                const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
-                rng.init(p.seed, pixel, p.sample_begin + k);
-                generate_ray(p.cam, rng, i, j, o, d);
-                thr = v3(1, 1, 1), rad = v3(0, 0, 0), depth = 0;
-                alive = true;
-            }
-            warp_next += min(avail, (uint32_t)__popc(dead));
-            if (exhausted && __ballot_sync(0xffffffffu, alive) == 0) break;
-        }
-        if (!alive) continue;
-
-        // ---- one path segment: ray.go:32-54 unrolled front to back ----
-        HitRec h;
-        trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads);
-        n_rays++;
-        bool done;
-        if (h.slot == RT_REF_NONE) {
-            rad = rad + thr * p.cam.background; // ray.go:53
-            done = true;
-        } else {
-            n_hits++;
-            V3 atten, emitted;
-            bool scattered;
-            if (QUADS && (h.slot & RT_HIT_QUAD)) {
-                const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
-                const uint32_t mi = __float_as_uint(q[1].w);
-                const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
-                scattered = shade_hit_quad(m0, m1, p.sc.tex, q, h.t, rng, o, d, atten, emitted);
-            } else {
-                const F4 s = sph[h.slot];
-                const int mi = meta[h.slot].y;
-                const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
-                scattered = shade_hit(m0, m1, p.sc.tex, s, h.t, rng, o, d, atten, emitted);
-            }
-            rad = rad + thr * emitted; // ray.go:41,50
-            if (!scattered) {
-                done = true; // ray.go:44-46
-            } else {
-                thr = thr * atten; // ray.go:48
-                depth++;
-                done = depth >= p.cam.max_depth; // ray.go:33-35
-            }
-        }
-        if (done) {
-            p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
-            alive = false;
-        }
-    }
-
-    // ---- work counters: warp shuffle reduction, one atomic per warp ----
-    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
-#pragma unroll
-    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
-        unsigned long long x = v[q];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0 && x) atomicAdd(p.stats + q, x);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// render megakernel, pool variant: each warp owns a pool of K*32 paths
-// ---------------------------------------------------------------------------------------------
-// The lock-step megakernel above keeps only ~12 of 32 lanes busy in traversal because rays of one
-// warp need very different numbers of node visits (9.5 +- 4.1, max 50).  Here a warp owns P = 32*K
-// paths.  A round is: (1) TRACE — the P rays sit in a shared-memory pool; a lane that finishes its
-// ray immediately fetches the next untraced one (dynamic fetch), so lanes stay busy until the pool
-// is drained; (2) SHADE — lane l shades its own paths l, l+32, ... (their state lives in its
-// registers), all lanes together, and regenerates finished paths from the warp's chunk of the path
-// index space.  The arithmetic of a path is the same functions in the same order as above, so the
-// image is bit-identical; only the scheduling differs.
-//
-// Pool entry of slot s (per warp): A[s] = (o.xyz, t)  B[s] = (d.xyz, bits(hit slot | RT_POOL_DEAD)).
-#define RT_POOL_DEAD 0xFFFFFFFEu
-
-static size_t pool_smem_bytes(const DevScene &s, int block, int K, bool scene_in_smem) {
-    size_t b = scene_in_smem ? scene_smem_bytes(s) + ((s.n_slots & 1) ? 8 : 0) : 0;
-    b += (size_t)(scene_in_smem ? s.stack_depth : 0) * block * 4; // traversal stacks
-    b = (b + 15) & ~(size_t)15;
-    return b + (size_t)block * K * 32; // pool: 2 x float4 per path
-}
-
-template <int BLOCK, int K, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(BLOCK, 1) render_pool_kernel(const __grid_constant__ RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr uint32_t P = 32u * K;
-    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats;
-    const I2 *meta = p.sc.meta;
-    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
-    Stack stack;
-    size_t used = 0;
-    if constexpr (SMEM) {
-        SmemScene s = stage_scene(p.sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, mats = s.mats, meta = s.meta;
-        stack.base = s.stack + threadIdx.x;
-        stack.stride = BLOCK;
-        used = (size_t)((unsigned char *)(s.stack + (size_t)p.sc.stack_depth * BLOCK) - smem_raw);
-        used = (used + 15) & ~(size_t)15;
-    }
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    float4 *poolA = reinterpret_cast<float4 *>(smem_raw + used) + (size_t)warp * 2 * P;
-    float4 *poolB = poolA + P;
-
-    // ---- per-lane state of the K paths this lane owns (slot = 32*k + lane) ----
-    V3 thr[K], rad[K];
-    uint32_t idx[K], blk[K]; // path index in the pass; next Philox block of the path's stream
-    int depth[K];
-    uint32_t alive = 0; // bit k: path k is in flight
-    uint32_t warp_next = 0, warp_end = 0;
-    bool exhausted = false;
-    unsigned long long n_rays = 0, n_hits = 0;
-    WorkCounters wc;
-    wc.box_tests = wc.sphere_tests = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        thr[k] = v3(1, 1, 1), rad[k] = v3(0, 0, 0), idx[k] = 0, blk[k] = 0, depth[k] = 0;
-        poolB[32 * k + lane] = make_float4(0, 0, 0, __uint_as_float(RT_POOL_DEAD));
-    }
-
-    // Regenerate path k of every lane that has none (camera.go:265-299), from the warp's chunk.
-    auto regenerate = [&](int k) {
-        const unsigned need = __ballot_sync(0xffffffffu, !((alive >> k) & 1u));
-        if (!need) return;
-        if (warp_next >= warp_end && !exhausted) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= p.total_paths) exhausted = true;
-            else warp_next = base, warp_end = min(base + RT_CHUNK, p.total_paths);
-        }
-        const uint32_t avail = warp_end - warp_next;
-        const uint32_t rank = __popc(need & lt_mask);
-        if (!((alive >> k) & 1u) && rank < avail) {
-            const uint32_t id = warp_next + rank;
-            const uint32_t pp = id / p.spp_pass, ks = id - pp * p.spp_pass;
-            const uint32_t pixel = p.pixel_begin + pp;
-            const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
-            PathRng rng;
-            rng.init(p.seed, pixel, p.sample_begin + ks);
-            V3 o, d;
-            generate_ray(p.cam, rng, i, j, o, d);
-            idx[k] = id, blk[k] = rng.block, depth[k] = 0;
-            thr[k] = v3(1, 1, 1), rad[k] = v3(0, 0, 0);
-            poolA[32 * k + lane] = make_float4(o.x, o.y, o.z, 0.0f);
-            poolB[32 * k + lane] = make_float4(d.x, d.y, d.z, 0.0f);
-            alive |= 1u << k;
-        }
-        warp_next += min(avail, (uint32_t)__popc(need));
-    };
-
-#pragma unroll
-    for (int k = 0; k < K; k++) regenerate(k);
-    __syncwarp();
-
-    while (__ballot_sync(0xffffffffu, alive != 0) != 0) {
-        // ================= TRACE: drain the pool with dynamic fetch =================
-        {
-            uint32_t cursor = 0; // warp-uniform: next untraced slot
-            bool has_ray = false;
-            uint32_t cur = 0, ref = RT_REF_NONE, best = RT_REF_NONE;
-            V3 o = v3(0, 0, 0), d = v3(0, 0, 0), inv = v3(0, 0, 0), noi = v3(0, 0, 0);
-            float a = 0, tbest = 0;
-            for (;;) {
-                const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
-                if (idle != 0 && cursor < P) {
-                    const uint32_t my = cursor + __popc(idle & lt_mask);
-                    if (!has_ray && my < P) {
-                        const float4 B = poolB[my];
-                        if (__float_as_uint(B.w) != RT_POOL_DEAD) {
-                            const float4 A = poolA[my];
-                            o = v3(A.x, A.y, A.z), d = v3(B.x, B.y, B.z);
-                            inv = v3(cull_rcp(d.x), cull_rcp(d.y), cull_rcp(d.z));
-                            noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-                            a = lensq(d);
-                            tbest = INFINITY, best = RT_REF_NONE, ref = p.sc.root_ref;
-                            stack.reset();
-                            cur = my, has_ray = true;
-                            n_rays++;
-                        }
-                    }
-                    cursor = min(P, cursor + (uint32_t)__popc(idle));
-                }
-                if (__ballot_sync(0xffffffffu, has_ray) == 0) {
-                    if (cursor >= P) break;
-                    continue;
-                }
-                if (has_ray) {
-                    // descend through inner nodes until this lane holds a leaf (or nothing)
-                    while (!(ref & RT_LEAF)) {
-                        const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1];
-                        const F4 r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
-                        float tl, tr;
-                        const bool hl = box_test(l0, l1, inv, noi, 0.001f, tbest, tl);
-                        const bool hr = box_test(r0, r1, inv, noi, 0.001f, tbest, tr);
-                        if (COUNT) wc.box_tests += 2;
-                        const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
-                        if (hl && hr) {
-                            const bool left_first = tl <= tr;
-                            stack.push(left_first ? rref : lref);
-                            ref = left_first ? lref : rref;
-                        } else if (hl) {
-                            ref = lref;
-                        } else if (hr) {
-                            ref = rref;
-                        } else {
-                            ref = stack.pop();
-                        }
-                    }
-                    if (ref != RT_REF_NONE) {
-                        const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
-                        for (uint32_t s = first; s < first + count; s++) {
-                            const F4 sp = sph[s];
-                            float t;
-                            if (COUNT) wc.sphere_tests += 1;
-                            if (!sphere_candidate(sp, o, d, a, 0.001f, t)) continue;
-                            if (t < tbest) {
-                                tbest = t, best = s;
-                            } else if (t == tbest && best != RT_REF_NONE) {
-                                if (meta[s].x < meta[best].x) best = s; // exact tie: earlier object wins
-                            }
-                        }
-                        ref = stack.pop();
-                    }
-                    if (ref == RT_REF_NONE) { // traversal finished: publish (t, hit slot) in the pool
-                        poolA[cur].w = tbest;
-                        poolB[cur].w = __uint_as_float(best);
-                        has_ray = false;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        // ================= SHADE: every lane advances its own K paths =================
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const uint32_t slot = 32u * k + lane;
-            if ((alive >> k) & 1u) {
-                const float4 A = poolA[slot], B = poolB[slot];
-                V3 o = v3(A.x, A.y, A.z), d = v3(B.x, B.y, B.z);
-                const uint32_t hs = __float_as_uint(B.w);
-                bool done;
-                if (hs == RT_REF_NONE) {
-                    rad[k] = rad[k] + thr[k] * p.cam.background; // ray.go:53
-                    done = true;
-                } else {
-                    n_hits++;
-                    const F4 s = sph[hs];
-                    const int mi = meta[hs].y;
-                    const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
-                    const uint32_t pp = idx[k] / p.spp_pass, ks = idx[k] - pp * p.spp_pass;
-                    PathRng rng;
-                    rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + ks);
-                    rng.block = blk[k];
-                    V3 atten, emitted;
-                    const bool scattered = shade_hit(m0, m1, p.sc.tex, s, A.w, rng, o, d, atten, emitted);
-                    blk[k] = rng.block;
-                    rad[k] = rad[k] + thr[k] * emitted; // ray.go:41,50
-                    if (!scattered) {
-                        done = true; // ray.go:44-46
-                    } else {
-                        thr[k] = thr[k] * atten; // ray.go:48
-                        depth[k]++;
-                        done = depth[k] >= p.cam.max_depth; // ray.go:33-35
-                    }
-                }
-                if (done) {
-                    p.samples[idx[k]] = make_float4(rad[k].x, rad[k].y, rad[k].z, 0.0f);
-                    alive &= ~(1u << k);
-                    poolB[slot].w = __uint_as_float(RT_POOL_DEAD);
-                } else {
-                    poolA[slot] = make_float4(o.x, o.y, o.z, 0.0f);
-                    poolB[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-                }
-            }
-            regenerate(k);
-        }
-        __syncwarp();
-    }
-
-    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
-#pragma unroll
-    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
-        unsigned long long x = v[q];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0 && x) atomicAdd(p.stats + q, x);
-    }
-}
-
-// accum[pixel] (+)= sum_k samples[(pixel - pixel_begin) * spp_pass + k], k ascending: the FP32
-// summation order of camera.go:255-260.  first_pass: start from zero instead of accum.
-__global__ void reduce_kernel(const float4 *__restrict__ samples, float *__restrict__ accum, uint32_t pixel_begin,
-                              uint32_t n_pixels, uint32_t spp_pass, int first_pass) {
-    const uint32_t pp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pp >= n_pixels) return;
-    float *a = accum + 3 * (size_t)(pixel_begin + pp);
-    V3 sum = first_pass ? v3(0, 0, 0) : v3(a[0], a[1], a[2]);
-    const float4 *s = samples + (size_t)pp * spp_pass;
-    for (uint32_t k = 0; k < spp_pass; k++) {
-        const float4 r = s[k];
-        sum = sum + v3(r.x, r.y, r.z);
-    }
-    a[0] = sum.x, a[1] = sum.y, a[2] = sum.z;
-}
-
-__global__ void resolve_kernel(const float *__restrict__ accum, uint8_t *__restrict__ rgb, uint32_t n_pixels,
-                               float inv_spp) {
-    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= n_pixels) return;
-    const float *a = accum + 3 * (size_t)pix;
-    uint8_t out[3];
-    resolve_pixel(v3(a[0], a[1], a[2]), inv_spp, out);
-    rgb[3 * (size_t)pix + 0] = out[0], rgb[3 * (size_t)pix + 1] = out[1], rgb[3 * (size_t)pix + 2] = out[2];
-}
-
-// ---------------------------------------------------------------------------------------------
-// parity hooks
-// ---------------------------------------------------------------------------------------------
-template <int BLOCK, bool SMEM, bool QUADS>
-__global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ DevScene sc, const float *__restrict__ origins,
-                                                      const float *__restrict__ dirs, long long n, float tmin, float tmax,
-                                                      int32_t *__restrict__ id_out, float *__restrict__ t_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const F4 *nodes = sc.nodes, *sph = sc.sph, *quads = sc.quads;
-    const I2 *meta = sc.meta;
-    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
-    Stack stack;
-    if constexpr (SMEM) {
-        SmemScene s = stage_scene(sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, quads = s.quads, meta = s.meta;
-        stack.base = s.stack + threadIdx.x;
-        stack.stride = BLOCK;
-    }
-    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
-        const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
-        const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
-        HitRec h;
-        trace_closest<Stack, false, QUADS>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, quads);
-        if (h.slot == RT_REF_NONE) {
-            id_out[i] = -1, t_out[i] = 0.0f;
-        } else {
-            id_out[i] = slot_object_id(h.slot, meta, quads), t_out[i] = h.t;
-        }
-    }
-}
-
-__global__ void primary_kernel(DevCamera cam, uint64_t seed, uint32_t pixel_begin, uint32_t sample_begin,
-                               uint32_t spp, long long n, float *__restrict__ origins, float *__restrict__ dirs) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const uint32_t pp = (uint32_t)(idx / spp), k = (uint32_t)(idx - (long long)pp * spp);
-    const uint32_t pixel = pixel_begin + pp;
-    const int j = (int)(pixel / (uint32_t)cam.width), i = (int)(pixel - (uint32_t)j * cam.width);
-    PathRng rng;
-    rng.init(seed, pixel, sample_begin + k);
-    V3 o, d;
-    generate_ray(cam, rng, i, j, o, d);
-    origins[3 * idx] = o.x, origins[3 * idx + 1] = o.y, origins[3 * idx + 2] = o.z;
-    dirs[3 * idx] = d.x, dirs[3 * idx + 1] = d.y, dirs[3 * idx + 2] = d.z;
-}
+#include "rt_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // host side: per-device workspace, shared by all scene handles of the process
@@ -1145,11 +644,6 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
 // ---------------------------------------------------------------------------------------------
 // one call, several GPUs (what a single host process such as the Go program needs)
 // ---------------------------------------------------------------------------------------------
-__global__ void add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = dst[i] + src[i];
-}
-
 // Sample-split inside the library: device k renders its share of camera->spp into its
 // own FP32 accumulator on its own host thread; the accumulators are peer-copied to devices[0] and
 // added in device order (deterministic), devices[0] resolves.  Every (pixel, sample) keeps the
