@@ -73,6 +73,8 @@ struct Workspace {
     size_t rgb_cap = 0, h_rgb_cap = 0; // bytes
     float *h_accum = nullptr;
     size_t h_accum_cap = 0; // floats (pinned)
+    float4 *queue = nullptr; // two-stage mode: 3 x capacity float4 (origin, direction, throughput)
+    size_t queue_cap = 0;    // elements per array
 };
 static Workspace g_ws[RT_MAX_DEVICES];
 
@@ -100,9 +102,10 @@ extern "C" void rt_workspace_release(int device) {
         if (device >= 0 && d != device) continue;
         Workspace &w = g_ws[d];
         std::lock_guard<std::mutex> lock(w.mu);
-        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum) continue;
+        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue) continue;
         cudaSetDevice(d);
-        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb);
+        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb), cudaFree(w.queue);
+        w.queue = nullptr, w.queue_cap = 0;
         if (w.h_rgb) cudaFreeHost(w.h_rgb);
         if (w.h_accum) cudaFreeHost(w.h_accum);
         w.samples = nullptr, w.accum = nullptr, w.rgb = nullptr, w.h_rgb = nullptr, w.h_accum = nullptr;
@@ -126,6 +129,10 @@ struct rt_scene {
     bool use_smem = false;
     int block = 256;
     int minb = 3;
+    bool use_split = false; // two-stage mode: coherent primary stage + megakernel on the survivors
+    unsigned int *d_queue_count = nullptr;
+    int primary_grid[2] = {0, 0};
+    size_t primary_smem[2] = {0, 0};
     bool use_pool = false; // pool-variant megakernel (RT_B200_KERNEL=pool)
     int pool_block = 512, pool_k = 4;
     // device buffers
@@ -234,7 +241,7 @@ static void free_scene(rt_scene *s) {
     cudaFree(s->d_nodes), cudaFree(s->d_sph), cudaFree(s->d_mats), cudaFree(s->d_meta), cudaFree(s->d_images);
     cudaFree(s->d_quads), cudaFree(s->d_perlins);
     for (auto p : s->d_texels) cudaFree(p);
-    cudaFree(s->d_counter), cudaFree(s->d_stats);
+    cudaFree(s->d_counter), cudaFree(s->d_stats), cudaFree(s->d_queue_count);
     for (auto e : s->events) cudaEventDestroy(e);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -323,6 +330,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
         }
     }
     CU(cudaMalloc(&s->d_counter, sizeof(unsigned int)));
+    CU(cudaMalloc(&s->d_queue_count, sizeof(unsigned int)));
     CU(cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long)));
     CU(cudaStreamSynchronize(s->stream));
 
@@ -338,6 +346,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     {
         const char *kv = getenv("RT_B200_KERNEL");
         s->use_pool = kv && std::string(kv) == "pool";
+        s->use_split = kv ? std::string(kv) == "split" : false;
         s->pool_block = env_int("RT_B200_POOL_BLOCK", 512);
         s->pool_k = env_int("RT_B200_POOL_K", 4);
     }
@@ -396,9 +405,26 @@ static double dist_to_center(const rt_scene *s, const float *p) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS>
+template <int BLOCK, bool SMEM, bool COUNT, bool QUADS>
+static int launch_primary_t(rt_scene *s, const RenderParams &p) {
+    auto kern = primary_stage_kernel<BLOCK, SMEM, COUNT, QUADS>;
+    if (s->primary_grid[COUNT] == 0) {
+        const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+        if (per_sm < 1) return fail(RT_ERR_CUDA, "primary stage does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
+        s->primary_grid[COUNT] = s->sm_count * per_sm;
+        s->primary_smem[COUNT] = smem;
+    }
+    kern<<<s->primary_grid[COUNT], BLOCK, s->primary_smem[COUNT], s->stream>>>(p);
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS, bool SPLIT = false>
 static int launch_render_t(rt_scene *s, const RenderParams &p) {
-    auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT, QUADS>;
+    auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT, QUADS, SPLIT>;
     if (s->grid_cache[COUNT] == 0) { // once per handle: opt in to the dynamic shared memory, size the grid
         const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -449,8 +475,18 @@ static int launch_pool_b(rt_scene *s, const RenderParams &p) {
     return launch_pool_t<512, 4, SMEM, COUNT>(s, p);
 }
 
+// two-stage mode: coherent primary stage, then the megakernel on the queued survivors
+template <bool SMEM, bool COUNT, bool QUADS>
+static int launch_split(rt_scene *s, const RenderParams &p) {
+    CU(cudaMemsetAsync(s->d_queue_count, 0, sizeof(unsigned int), s->stream));
+    int rc = launch_primary_t<256, SMEM, COUNT, QUADS>(s, p);
+    if (rc != RT_OK) return rc;
+    return launch_render_t<256, 3, SMEM, COUNT, QUADS, true>(s, p);
+}
+
 template <bool SMEM, bool COUNT>
 static int launch_render_q(rt_scene *s, const RenderParams &p) {
+    if (s->use_split) return s->has_quads ? launch_split<SMEM, COUNT, true>(s, p) : launch_split<SMEM, COUNT, false>(s, p);
     if (s->has_quads) return launch_render_b<SMEM, COUNT, true>(s, p);
     if (s->use_pool) return launch_pool_b<SMEM, COUNT>(s, p); // experimental pool variant: spheres only
     return launch_render_b<SMEM, COUNT, false>(s, p);
@@ -500,6 +536,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     const size_t need = (size_t)pix_tile * std::min<uint32_t>(spp_pass_max, (uint32_t)spp);
     Workspace &ws = g_ws[s->device];
     rc = ws_reserve(ws.samples, ws.samples_cap, need);
+    if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, 3 * need);
     if (rc != RT_OK) return rc;
     CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), s->stream));
 
@@ -517,6 +554,8 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.counter = s->d_counter;
     p.stats = s->d_stats;
     p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", 8)));
+    p.queue_o = ws.queue, p.queue_d = ws.queue ? ws.queue + need : nullptr, p.queue_t = ws.queue ? ws.queue + 2 * need : nullptr;
+    p.queue_count = s->d_queue_count;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
         for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {
@@ -535,7 +574,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
             n_ev += 2;
             reduce_kernel<<<(np + 127) / 128, 128, 0, s->stream>>>(ws.samples, d_accum, pb, np, sp, k0 == 0);
             CU(cudaGetLastError());
-            *launches += 2;
+            *launches += s->use_split ? 3 : 2;
         }
     }
     if (stats) {

@@ -95,12 +95,18 @@ struct RenderParams {
     unsigned int *counter; // next unclaimed path index
     unsigned long long *stats; // rays, hits, box tests, sphere tests
     uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
+    // two-stage mode (primary_stage_kernel + render_kernel<SPLIT>): paths that survive their first
+    // segment, as three float4 arrays of capacity total_paths
+    float4 *queue_o;           // (o.xyz, bits path index)
+    float4 *queue_d;           // (d.xyz, bits next Philox block)
+    float4 *queue_t;           // (throughput.xyz, 0)
+    unsigned int *queue_count; // entries appended by the primary stage
 };
 
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
 
 // BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
-template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS>
+template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS, bool SPLIT = false>
 __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
@@ -121,6 +127,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t warp_next = 0, warp_end = 0;
     bool exhausted = false;
+    // work items: all paths of the pass, or (two-stage mode) the survivors queued by the primary stage
+    const uint32_t total_items = SPLIT ? *p.queue_count : p.total_paths;
 
     bool alive = false;
     uint32_t idx = 0;
@@ -140,23 +148,38 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= p.total_paths) {
+                if (base >= total_items) {
                     exhausted = true;
                 } else {
                     warp_next = base;
-                    warp_end = min(base + RT_CHUNK, p.total_paths);
+                    warp_end = min(base + RT_CHUNK, total_items);
                 }
             }
             const uint32_t avail = warp_end - warp_next;
             const uint32_t rank = __popc(dead & lt_mask);
             if (!alive && rank < avail) {
-                idx = warp_next + rank;
-                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-                const uint32_t pixel = p.pixel_begin + pp;
-                const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
-                rng.init(p.seed, pixel, p.sample_begin + k);
-                generate_ray(p.cam, rng, i, j, o, d);
-                thr = v3(1, 1, 1), rad = v3(0, 0, 0), depth = 0;
+                if (SPLIT) { // resume a path after its first segment
+                    const uint32_t e = warp_next + rank;
+                    const float4 qo = p.queue_o[e], qd = p.queue_d[e], qt = p.queue_t[e];
+                    idx = __float_as_uint(qo.w);
+                    const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                    rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + k);
+                    rng.block = __float_as_uint(qd.w);
+                    o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z);
+                    thr = v3(qt.x, qt.y, qt.z), rad = v3(0, 0, 0), depth = 1;
+                    if (qt.w != 0.0f) { // radiance emitted on the first segment (no reference material does this)
+                        const float4 r0 = p.samples[idx];
+                        rad = v3(r0.x, r0.y, r0.z);
+                    }
+                } else {
+                    idx = warp_next + rank;
+                    const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                    const uint32_t pixel = p.pixel_begin + pp;
+                    const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+                    rng.init(p.seed, pixel, p.sample_begin + k);
+                    generate_ray(p.cam, rng, i, j, o, d);
+                    thr = v3(1, 1, 1), rad = v3(0, 0, 0), depth = 0;
+                }
                 alive = true;
             }
             warp_next += min(avail, (uint32_t)__popc(dead));
@@ -203,6 +226,101 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
     }
 
     // ---- work counters: warp shuffle reduction, one atomic per warp ----
+    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
+#pragma unroll
+    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
+        unsigned long long x = v[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0 && x) atomicAdd(p.stats + q, x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// two-stage mode, stage 1: the first segment of every path, traced as coherent warps
+// ---------------------------------------------------------------------------------------------
+// Consecutive lanes hold consecutive samples of one pixel, so the 32 primary rays of a warp walk the
+// BVH almost identically (measured: ~0.9 lane efficiency against ~0.4 for mixed-depth warps).  Each
+// thread generates its camera ray (camera.go:265-299), traces it and applies the first Emit + Scatter
+// (ray.go:37-50).  A path that ends here (miss, absorbed, emitter, depth limit) writes its radiance;
+// a survivor is appended to the queue (warp-aggregated atomic) and finished by render_kernel<SPLIT>.
+// Same functions, same order per path as the one-stage kernel: the image is bit-identical.
+template <int BLOCK, bool SMEM, bool COUNT, bool QUADS>
+__global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_constant__ RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
+    const I2 *meta = p.sc.meta;
+    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
+    Stack stack;
+    if constexpr (SMEM) {
+        SmemScene s = stage_scene(p.sc, smem_raw);
+        nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta;
+        stack.base = s.stack + threadIdx.x;
+        stack.stride = BLOCK;
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long n_rays = 0, n_hits = 0;
+    WorkCounters wc;
+    wc.box_tests = wc.sphere_tests = 0;
+    // whole warps iterate together (the trip count is warp-uniform), lanes past the end idle
+    const uint32_t n_rounds = (p.total_paths + BLOCK * gridDim.x - 1) / (BLOCK * gridDim.x);
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        const uint32_t idx = (r * gridDim.x + blockIdx.x) * BLOCK + threadIdx.x;
+        bool survive = false, carries = false;
+        V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1);
+        uint32_t block = 0;
+        if (idx < p.total_paths) {
+            const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+            const uint32_t pixel = p.pixel_begin + pp;
+            const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+            PathRng rng;
+            rng.init(p.seed, pixel, p.sample_begin + k);
+            generate_ray(p.cam, rng, i, j, o, d);
+            HitRec h;
+            trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads);
+            n_rays++;
+            V3 rad = v3(0, 0, 0);
+            if (h.slot == RT_REF_NONE) {
+                rad = rad + thr * p.cam.background; // ray.go:53
+            } else {
+                n_hits++;
+                V3 atten, emitted;
+                bool scattered;
+                if (QUADS && (h.slot & RT_HIT_QUAD)) {
+                    const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
+                    const uint32_t mi = __float_as_uint(q[1].w);
+                    scattered = shade_hit_quad(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, q, h.t, rng, o, d, atten, emitted);
+                } else {
+                    const F4 s = sph[h.slot];
+                    const int mi = meta[h.slot].y;
+                    scattered = shade_hit(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, s, h.t, rng, o, d, atten, emitted);
+                }
+                rad = rad + thr * emitted; // ray.go:41,50
+                if (scattered) {
+                    thr = thr * atten; // ray.go:48
+                    survive = 1 < p.cam.max_depth; // ray.go:33-35 with depth = 1
+                }
+            }
+            block = rng.block;
+            // no material of the reference both emits and scatters, so a survivor normally carries no
+            // radiance; if one ever does, it is parked in the sample slot and flagged in the queue entry
+            carries = survive && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f);
+            if (!survive || carries) p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
+        }
+        // append survivors: one atomic per warp, consecutive entries for consecutive lanes
+        const unsigned m = __ballot_sync(0xffffffffu, survive);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(p.queue_count, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (survive) {
+                const uint32_t e = base + __popc(m & ((1u << lane) - 1u));
+                p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
+                p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block));
+                p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, carries ? 1.0f : 0.0f);
+            }
+        }
+    }
     unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
 #pragma unroll
     for (int q = 0; q < (COUNT ? 4 : 2); q++) {
