@@ -306,7 +306,8 @@ def main():
     achieved = instr_per_sample * samples_per_launch / (mk_ms_per_launch * 1e-3) / 1e12
     smem_bw = bytes_per_ray * (rays / world / args.steps) / (mk_ms / args.steps * 1e-3) / 1e9
     roofline = {
-        "bound": "fp32_issue", "kernel": "render_kernel", "achieved": achieved, "peak": peak_instr,
+        "bound": "fp32_issue", "kernel": "primary_stage_kernel + render_kernel<SPLIT> (timed together, per pass)",
+        "achieved": achieved, "peak": peak_instr,
         "unit": "T lane-instr/s", "frac": achieved / peak_instr,
         # dram__bytes_read.sum + dram__bytes_write.sum of one render_kernel launch of 31.59 M paths (39 spp x
         # 810 000 px, the C2 pass size), ncu --set full, profiles/r01i_render_kernel_ncu_full.txt; the

@@ -346,7 +346,8 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     {
         const char *kv = getenv("RT_B200_KERNEL");
         s->use_pool = kv && std::string(kv) == "pool";
-        s->use_split = kv ? std::string(kv) == "split" : false;
+        // default: two-stage ("split"); RT_B200_KERNEL=mega selects the one-stage megakernel
+        s->use_split = kv ? std::string(kv) == "split" : true;
         s->pool_block = env_int("RT_B200_POOL_BLOCK", 512);
         s->pool_k = env_int("RT_B200_POOL_K", 4);
     }
@@ -553,7 +554,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.samples = ws.samples;
     p.counter = s->d_counter;
     p.stats = s->d_stats;
-    p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", 8)));
+    p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", s->use_split ? 1 : 8)));
     p.queue_o = ws.queue, p.queue_d = ws.queue ? ws.queue + need : nullptr, p.queue_t = ws.queue ? ws.queue + 2 * need : nullptr;
     p.queue_count = s->d_queue_count;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
