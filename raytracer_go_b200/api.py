@@ -404,6 +404,16 @@ class Camera:
             writer.write("\n".join("%d %d %d" % (p[0], p[1], p[2]) for p in px[b:b + 5000]) + "\n")
         return None
 
+    def RenderP6(self, world, writer):
+        """Binary PPM (the reference's TODO at camera.go:196: its P3 text is ~12 bytes per pixel and,
+        at 4K, costs more host time than the GPU render).  `writer` takes bytes."""
+        w, h = self.c.width, self.c.height
+        with Scene(flatten_world(world), self.device) as sc:
+            rgb, _, self.last_stats = sc.render(self.c, self.seed)
+        writer.write(b"P6\n%d %d\n255\n" % (w, h))
+        writer.write(rgb.tobytes())
+        return None
+
 
 def NewCamera(aspectRatio, imageWidth, *opts, seed=scenes.RENDER_SEED, device=0):
     """camera.go:104-126 with its defaults."""

@@ -193,8 +193,9 @@ struct Camera {
     int device = 0;
     rt_stats last_stats{};
 
-    // camera.go:180: returns "" for Go's nil error, the message otherwise.
-    std::string Render(const std::shared_ptr<BVH> &world, std::ostream &writer) {
+    // camera.go:180: returns "" for Go's nil error, the message otherwise.  binary = false writes the
+    // reference's P3 text; binary = true writes P6 (the reference's TODO at camera.go:196).
+    std::string Render(const std::shared_ptr<BVH> &world, std::ostream &writer, bool binary = false) {
         // flatten: materials / textures de-duplicated by pointer, spheres in insertion order
         std::vector<rt_sphere> spheres;
         std::vector<rt_quad> quads;
@@ -281,6 +282,11 @@ struct Camera {
         std::string err = rc == RT_OK ? "" : rt_last_error();
         rt_scene_destroy(scene);
         if (!err.empty()) return err;
+        if (binary) {
+            writer << "P6\n" << w << " " << h << "\n255\n";
+            writer.write(reinterpret_cast<const char *>(rgb.data()), (std::streamsize)rgb.size());
+            return writer ? "" : "write failed";
+        }
         // camera.go:183-188 header, then one "R G B" line per pixel in chunks of 5000 (camera.go:225, 242)
         writer << "P3\n" << w << " " << h << "\n255\n";
         std::string chunk;

@@ -372,3 +372,18 @@ def test_render_multi_two_devices(gpu, random_scene):
     assert (np.abs(rgb2.astype(int) - rgb.astype(int)) <= 1).all()
     rgb3, acc3, _ = api.render_multi(random_scene, cam, [1, 0], SEED, want_accum=True)
     assert np.allclose(acc3, acc, rtol=2e-6, atol=1e-6)
+
+
+def test_binary_ppm_equals_text_ppm(gpu):
+    """RenderP6 (binary PPM, the reference's TODO at camera.go:196) carries the pixels of Render's P3."""
+    import io
+    world = _splitmix_scene()
+    cam = api.NewCamera(16.0 / 9.0, 96, api.WithSamplesPerPixel(2), api.WithLookFrom(api.NewVec3(13, 2, 3)),
+                        api.WithFOVDegrees(20), api.WithBackgroundColor(api.NewVec3(0.7, 0.8, 1)))
+    t, b = io.StringIO(), io.BytesIO()
+    cam.Render(api.NewBVHFromWorld(world), t)
+    cam.RenderP6(api.NewBVHFromWorld(world), b)
+    text = np.array(t.getvalue().split()[4:], np.uint8)
+    raw = b.getvalue()
+    assert raw.startswith(b"P6\n96 54\n255\n")
+    assert np.array_equal(np.frombuffer(raw[len(b"P6\n96 54\n255\n"):], np.uint8), text)
