@@ -309,11 +309,13 @@ def main():
         "bound": "fp32_issue", "kernel": "primary_stage_kernel + render_kernel<SPLIT> (timed together, per pass)",
         "achieved": achieved, "peak": peak_instr,
         "unit": "T lane-instr/s", "frac": achieved / peak_instr,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one render_kernel launch of 31.59 M paths (39 spp x
-        # 810 000 px, the C2 pass size), ncu --set full, profiles/r01i_render_kernel_ncu_full.txt; the
-        # algorithmic figure is the 16-byte radiance record each path writes
-        "traffic": {"dram_bytes_per_launch": 452.7e6, "algorithmic_bytes_per_launch": 16 * 31.59e6,
-                    "source": "profiles/r01i_render_kernel_ncu_full.txt (C2 pass: 39 spp x 1200x675)"}
+        # dram__bytes_read.sum + dram__bytes_write.sum of one C2 pass (31.59 M paths = 39 spp x 810 000 px):
+        # primary_stage_kernel 1.294 GB + render_kernel<SPLIT> 1.690 GB, ncu --set full,
+        # profiles/r01n_kernels_ncu_full.txt.  Algorithmic: a 16-byte radiance record per path plus a
+        # 48-byte queue entry written and read once per path that survives its first segment (83 %).
+        "traffic": {"dram_bytes_per_launch": 2.984e9,
+                    "algorithmic_bytes_per_launch": 16 * 31.59e6 + 96 * 0.83 * 31.59e6,
+                    "source": "profiles/r01n_kernels_ncu_full.txt (C2 pass: 39 spp x 1200x675)"}
         if args.config == "C2" and not args.width else None,
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz {peaks['sm_max_mhz']:.0f} ({peak_src} MEASURED_PEAKS.json clock)",
         "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": n_box,

@@ -19,13 +19,18 @@ from collections import defaultdict
 def main():
     rep, lib, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kern}"],
-                         capture_output=True, text=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-    hdr = rows[hdr_i]
-    kname = rows[hdr_i - 1][1]
-    body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    # the page lists one section per profiled launch: "Kernel Name" row, header row, one row per SASS instruction
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sect = next((i for i in starts if kern in rows[i][1]), None)
+    if sect is None:
+        print("no profiled kernel matches", kern, file=sys.stderr)
+        return 1
+    kname = rows[sect][1]
+    hdr = rows[sect + 1]
+    end = min([i for i in starts if i > sect] + [len(rows)])
+    body = [r for r in rows[sect + 2:end] if len(r) == len(hdr)]
     col = {h: i for i, h in enumerate(hdr)}
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, capture_output=True)
