@@ -73,8 +73,8 @@ struct Workspace {
     size_t rgb_cap = 0, h_rgb_cap = 0; // bytes
     float *h_accum = nullptr;
     size_t h_accum_cap = 0; // floats (pinned)
-    float4 *queue = nullptr; // two-stage mode: 3 x capacity float4 (origin, direction, throughput)
-    size_t queue_cap = 0;    // elements per array
+    float4 *queue = nullptr; // staged mode: 2 (ping-pong) x 3 x capacity float4 (origin, direction, throughput)
+    size_t queue_cap = 0;    // elements in total
 };
 static Workspace g_ws[RT_MAX_DEVICES];
 
@@ -130,9 +130,10 @@ struct rt_scene {
     int block = 256;
     int minb = 3;
     bool use_split = false; // two-stage mode: coherent primary stage + megakernel on the survivors
-    unsigned int *d_queue_count = nullptr;
-    int primary_grid[2] = {0, 0};
-    size_t primary_smem[2] = {0, 0};
+    unsigned int *d_queue_count = nullptr; // RT_MAX_STAGES counters, one per stage queue
+    int n_stages = 1;                      // coherent stages before the megakernel (RT_B200_STAGES)
+    int primary_grid[2][2] = {{0, 0}, {0, 0}}; // [COUNT][FIRST]
+    size_t primary_smem[2][2] = {{0, 0}, {0, 0}};
     bool use_pool = false; // pool-variant megakernel (RT_B200_KERNEL=pool)
     int pool_block = 512, pool_k = 4;
     // device buffers
@@ -330,7 +331,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
         }
     }
     CU(cudaMalloc(&s->d_counter, sizeof(unsigned int)));
-    CU(cudaMalloc(&s->d_queue_count, sizeof(unsigned int)));
+    CU(cudaMalloc(&s->d_queue_count, RT_MAX_STAGES * sizeof(unsigned int)));
     CU(cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long)));
     CU(cudaStreamSynchronize(s->stream));
 
@@ -348,6 +349,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
         s->use_pool = kv && std::string(kv) == "pool";
         // default: two-stage ("split"); RT_B200_KERNEL=mega selects the one-stage megakernel
         s->use_split = kv ? std::string(kv) == "split" : true;
+        s->n_stages = std::min(RT_MAX_STAGES, std::max(1, env_int("RT_B200_STAGES", 1)));
         s->pool_block = env_int("RT_B200_POOL_BLOCK", 512);
         s->pool_k = env_int("RT_B200_POOL_K", 4);
     }
@@ -406,19 +408,19 @@ static double dist_to_center(const rt_scene *s, const float *p) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK, bool SMEM, bool COUNT, bool QUADS>
+template <int BLOCK, bool SMEM, bool COUNT, bool QUADS, bool FIRST>
 static int launch_primary_t(rt_scene *s, const RenderParams &p) {
-    auto kern = primary_stage_kernel<BLOCK, SMEM, COUNT, QUADS>;
-    if (s->primary_grid[COUNT] == 0) {
+    auto kern = primary_stage_kernel<BLOCK, SMEM, COUNT, QUADS, FIRST>;
+    if (s->primary_grid[COUNT][FIRST] == 0) {
         const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
         if (per_sm < 1) return fail(RT_ERR_CUDA, "primary stage does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
-        s->primary_grid[COUNT] = s->sm_count * per_sm;
-        s->primary_smem[COUNT] = smem;
+        s->primary_grid[COUNT][FIRST] = s->sm_count * per_sm;
+        s->primary_smem[COUNT][FIRST] = smem;
     }
-    kern<<<s->primary_grid[COUNT], BLOCK, s->primary_smem[COUNT], s->stream>>>(p);
+    kern<<<s->primary_grid[COUNT][FIRST], BLOCK, s->primary_smem[COUNT][FIRST], s->stream>>>(p);
     CU(cudaGetLastError());
     return RT_OK;
 }
@@ -476,12 +478,28 @@ static int launch_pool_b(rt_scene *s, const RenderParams &p) {
     return launch_pool_t<512, 4, SMEM, COUNT>(s, p);
 }
 
-// two-stage mode: coherent primary stage, then the megakernel on the queued survivors
+// staged mode: n_stages coherent stage kernels (segment 0 from the camera, segment k from the queue of
+// stage k-1, ping-pong buffers), then the megakernel on the survivors of the last stage
 template <bool SMEM, bool COUNT, bool QUADS>
-static int launch_split(rt_scene *s, const RenderParams &p) {
-    CU(cudaMemsetAsync(s->d_queue_count, 0, sizeof(unsigned int), s->stream));
-    int rc = launch_primary_t<256, SMEM, COUNT, QUADS>(s, p);
-    if (rc != RT_OK) return rc;
+static int launch_split(rt_scene *s, const RenderParams &p0) {
+    RenderParams p = p0;
+    CU(cudaMemsetAsync(s->d_queue_count, 0, RT_MAX_STAGES * sizeof(unsigned int), s->stream));
+    const size_t cap = (size_t)p.total_paths; // entries per array; layout: [buffer][o|d|t][cap]
+    float4 *buf[2] = {p.queue_o, p.queue_o + 3 * p.queue_stride};
+    for (int k = 0; k < s->n_stages; k++) {
+        float4 *out = buf[k & 1];
+        const float4 *in = buf[(k & 1) ^ 1];
+        p.queue_o = out, p.queue_d = out + p.queue_stride, p.queue_t = out + 2 * p.queue_stride;
+        p.queue_count = s->d_queue_count + k;
+        p.in_o = in, p.in_d = in + p.queue_stride, p.in_t = in + 2 * p.queue_stride;
+        p.in_count = k ? s->d_queue_count + k - 1 : nullptr;
+        p.stage_depth = k;
+        int rc = k == 0 ? launch_primary_t<256, SMEM, COUNT, QUADS, true>(s, p)
+                        : launch_primary_t<256, SMEM, COUNT, QUADS, false>(s, p);
+        if (rc != RT_OK) return rc;
+    }
+    (void)cap;
+    p.stage_depth = s->n_stages; // the megakernel resumes the survivors of the last stage
     return launch_render_t<256, 3, SMEM, COUNT, QUADS, true>(s, p);
 }
 
@@ -537,7 +555,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     const size_t need = (size_t)pix_tile * std::min<uint32_t>(spp_pass_max, (uint32_t)spp);
     Workspace &ws = g_ws[s->device];
     rc = ws_reserve(ws.samples, ws.samples_cap, need);
-    if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, 3 * need);
+    if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, (s->n_stages > 1 ? 6 : 3) * need);
     if (rc != RT_OK) return rc;
     CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), s->stream));
 
@@ -555,8 +573,9 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.counter = s->d_counter;
     p.stats = s->d_stats;
     p.regen_min = (uint32_t)std::min(32, std::max(1, env_int("RT_B200_REGEN_MIN", s->use_split ? 1 : 8)));
-    p.queue_o = ws.queue, p.queue_d = ws.queue ? ws.queue + need : nullptr, p.queue_t = ws.queue ? ws.queue + 2 * need : nullptr;
-    p.queue_count = s->d_queue_count;
+    p.queue_o = ws.queue, p.queue_stride = need; // launch_split fills the per-stage pointers
+    p.queue_d = p.queue_t = nullptr, p.queue_count = s->d_queue_count;
+    p.in_o = p.in_d = p.in_t = nullptr, p.in_count = nullptr, p.stage_depth = 0;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
         for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {
@@ -575,7 +594,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
             n_ev += 2;
             reduce_kernel<<<(np + 127) / 128, 128, 0, s->stream>>>(ws.samples, d_accum, pb, np, sp, k0 == 0);
             CU(cudaGetLastError());
-            *launches += s->use_split ? 3 : 2;
+            *launches += s->use_split ? 2 + s->n_stages : 2;
         }
     }
     if (stats) {

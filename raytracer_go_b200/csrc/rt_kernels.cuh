@@ -100,10 +100,16 @@ struct RenderParams {
     float4 *queue_o;           // (o.xyz, bits path index)
     float4 *queue_d;           // (d.xyz, bits next Philox block)
     float4 *queue_t;           // (throughput.xyz, 0)
-    unsigned int *queue_count; // entries appended by the primary stage
+    unsigned int *queue_count; // entries appended by the stage that fills queue_o/d/t
+    // stage k > 0 of the staged mode reads the survivors of stage k-1 here (same layout)
+    const float4 *in_o, *in_d, *in_t;
+    const unsigned int *in_count;
+    int stage_depth; // segments already traced for the paths a stage kernel processes
+    size_t queue_stride; // elements per queue array (host-side bookkeeping)
 };
 
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
+#define RT_MAX_STAGES 8 /* coherent stage kernels before the megakernel (staged mode) */
 
 // BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
 template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS, bool SPLIT = false>
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                     rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + k);
                     rng.block = __float_as_uint(qd.w);
                     o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z);
-                    thr = v3(qt.x, qt.y, qt.z), rad = v3(0, 0, 0), depth = 1;
+                    thr = v3(qt.x, qt.y, qt.z), rad = v3(0, 0, 0), depth = p.stage_depth;
                     if (qt.w != 0.0f) { // radiance emitted on the first segment (no reference material does this)
                         const float4 r0 = p.samples[idx];
                         rad = v3(r0.x, r0.y, r0.z);
@@ -245,7 +251,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 // (ray.go:37-50).  A path that ends here (miss, absorbed, emitter, depth limit) writes its radiance;
 // a survivor is appended to the queue (warp-aggregated atomic) and finished by render_kernel<SPLIT>.
 // Same functions, same order per path as the one-stage kernel: the image is bit-identical.
-template <int BLOCK, bool SMEM, bool COUNT, bool QUADS>
+// FIRST = false: the same for a later segment — the rays come from the previous stage's queue (in
+// pixel-neighbour order, all lanes alive) instead of the camera.
+template <int BLOCK, bool SMEM, bool COUNT, bool QUADS, bool FIRST = true>
 __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
@@ -263,23 +271,38 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
     WorkCounters wc;
     wc.box_tests = wc.sphere_tests = 0;
     // whole warps iterate together (the trip count is warp-uniform), lanes past the end idle
-    const uint32_t n_rounds = (p.total_paths + BLOCK * gridDim.x - 1) / (BLOCK * gridDim.x);
+    const uint32_t n_items = FIRST ? p.total_paths : *p.in_count;
+    const uint32_t n_rounds = (n_items + BLOCK * gridDim.x - 1) / (BLOCK * gridDim.x);
     for (uint32_t r = 0; r < n_rounds; r++) {
-        const uint32_t idx = (r * gridDim.x + blockIdx.x) * BLOCK + threadIdx.x;
+        const uint32_t item = (r * gridDim.x + blockIdx.x) * BLOCK + threadIdx.x;
+        uint32_t idx = item;
         bool survive = false, carries = false;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1);
         uint32_t block = 0;
-        if (idx < p.total_paths) {
-            const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-            const uint32_t pixel = p.pixel_begin + pp;
-            const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+        if (item < n_items) {
             PathRng rng;
-            rng.init(p.seed, pixel, p.sample_begin + k);
-            generate_ray(p.cam, rng, i, j, o, d);
+            V3 rad = v3(0, 0, 0);
+            if (FIRST) {
+                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                const uint32_t pixel = p.pixel_begin + pp;
+                const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+                rng.init(p.seed, pixel, p.sample_begin + k);
+                generate_ray(p.cam, rng, i, j, o, d);
+            } else {
+                const float4 qo = p.in_o[item], qd = p.in_d[item], qt = p.in_t[item];
+                idx = __float_as_uint(qo.w);
+                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + k);
+                rng.block = __float_as_uint(qd.w);
+                o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z), thr = v3(qt.x, qt.y, qt.z);
+                if (qt.w != 0.0f) { // radiance parked by an earlier stage
+                    const float4 r0 = p.samples[idx];
+                    rad = v3(r0.x, r0.y, r0.z);
+                }
+            }
             HitRec h;
             trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads);
             n_rays++;
-            V3 rad = v3(0, 0, 0);
             if (h.slot == RT_REF_NONE) {
                 rad = rad + thr * p.cam.background; // ray.go:53
             } else {
@@ -298,7 +321,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 rad = rad + thr * emitted; // ray.go:41,50
                 if (scattered) {
                     thr = thr * atten; // ray.go:48
-                    survive = 1 < p.cam.max_depth; // ray.go:33-35 with depth = 1
+                    survive = p.stage_depth + 1 < p.cam.max_depth; // ray.go:33-35
                 }
             }
             block = rng.block;
