@@ -197,10 +197,11 @@ int rt_abi_version(void);
 /* Number of usable sm_100 devices (0 when there is none; never negative). */
 int rt_device_count(void);
 
-/* Replaces NewWorld/World.Add/NewBVHFromWorld (hittables.go:44-53, bvh.go:138-185) for the
- * sphere subset: validates, builds the device BVH on the host (binned SAH; topology is free,
- * closest-hit semantics are World.Hit's, hittables.go:55-72), flattens it to 32-byte nodes in
- * depth-first order, and uploads nodes / spheres / materials / texels once. */
+/* Replaces NewWorld / World.Add / NewSphere / NewQuad / Box / NewBVHFromWorld (hittables.go:44-53,
+ * 85-94, 149-165, 200-216, bvh.go:138-185): validates, derives the quads' w / normal / D, builds the
+ * device BVH on the host (binned SAH; topology is free, closest-hit semantics are World.Hit's,
+ * hittables.go:55-72), flattens it to 32-byte nodes in depth-first order, and uploads nodes / spheres /
+ * quads / materials / texels / Perlin tables once. */
 int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out);
 void rt_scene_destroy(rt_scene *scene);
 /* Frees the per-device work buffers the library caches across handles (per-pass radiance buffer,

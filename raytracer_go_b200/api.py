@@ -337,7 +337,7 @@ def flatten_world(world):
             quads.append((h.Q, h.u, h.v, mat_id(h.material)))
             quad_ids.append(k)
         else:
-            raise TypeError(f"hittable {type(h).__name__} is outside the accelerated path (SURVEY §8f)")
+            raise TypeError(f"hittable {type(h).__name__} is not a Sphere or a Quad")
     return scenes.SceneData(np.array(spheres, scenes.SPHERE_DT).reshape(-1),
                             np.array(materials, scenes.MATERIAL_DT).reshape(-1),
                             np.array(textures, scenes.TEXTURE_DT).reshape(-1), images,
