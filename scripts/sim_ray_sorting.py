@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""Design exploration (not part of the product or the tests): how much lane efficiency ray ordering
+could buy in the lock-step traversal loop, replayed on real C2 path segments with their origins and
+directions (tests/hostsim: hs_traversal_events_rays).  Results:
+profiles/experiments/r01_lane_efficiency_simulations.txt.  Run from the repo root; ~10 minutes."""
 import ctypes as C, numpy as np, random, sys
 sys.path.insert(0,'/root/repo')
 from raytracer_go_b200 import scenes

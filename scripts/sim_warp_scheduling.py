@@ -1,4 +1,45 @@
-import pickle, numpy as np, random
+#!/usr/bin/env python
+"""Design exploration (not part of the product or the tests): replays the traversal event traces of
+real C2 path segments (tests/hostsim: hs_traversal_events) under different warp-scheduling policies
+and prints the lane efficiency each would reach.  Results: profiles/experiments/r01_lane_efficiency_simulations.txt.
+Run from the repo root after `make -C tests/hostsim`; takes a few minutes (pure Python)."""
+import ctypes as C
+import os
+import pickle
+import random
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+TRACES = "/tmp/rays_events.pkl"
+
+
+def record_traces():
+    from raytracer_go_b200 import scenes
+    from oracle import pyoracle as orc
+    hs = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/hostsim/libhostsim.so"))
+    hs.hs_traversal_events.restype = C.c_int64
+    s = scenes.random_scene()
+    desc, keep = s.to_desc()
+    cam = orc.camera_from_options(scenes.camera_options(1200, 8))
+    n_tok = 40_000_000
+    tok = np.zeros(n_tok, np.int8)
+    out = []
+    for r in np.linspace(0, cam.height - 1, 24).astype(int):
+        nr = C.c_int64()
+        n = hs.hs_traversal_events(C.byref(desc), C.byref(cam), C.c_uint64(7), 8, C.c_int64(int(r) * cam.width),
+                                   C.c_int64(cam.width), 4, tok.ctypes.data_as(C.c_void_p), C.c_int64(n_tok), C.byref(nr))
+        t = tok[:n].copy()
+        start = 0
+        for e in np.nonzero(t == 0)[0]:
+            out.append(t[start:e])
+            start = e + 1
+    pickle.dump(out, open(TRACES, "wb"))
+
+
+if not os.path.exists(TRACES):
+    record_traces()
 rays = pickle.load(open('/tmp/rays_events.pkl','rb'))
 rays = [r for r in rays if len(r)]
 random.seed(1)
@@ -149,45 +190,3 @@ for K in (1,4,8):
         for th in (0.35,0.5,0.65):
             run(f'spec M={M} thresh {th}', lambda pr: sim_spec(pr,M,th), K, trials=150)
 
-def sim_spec2(pool_rays, M=1, thresh=0.5, fetch_cost=4):
-    """as sim_spec but idle lanes fetch a new ray at every inner iteration (cost fetch_cost/iter)."""
-    P=len(pool_rays); nxt=0; lanes=[None]*32; cost=0
-    def fetch():
-        nonlocal nxt
-        for i in range(32):
-            if lanes[i] is None and nxt < P: lanes[i]=[pool_rays[nxt],0,0,[]]; nxt+=1
-    while True:
-        fetch()
-        act=[l for l in lanes if l is not None]
-        if not act: break
-        while True:
-            for i in range(32):
-                l=lanes[i]
-                if l is not None and l[1]>=len(l[0]) and not l[3]: lanes[i]=None
-            fetch()
-            act=[l for l in lanes if l is not None]
-            for l in act:
-                r=l[0]
-                while l[1]<len(r) and r[l[1]]<0 and len(l[3])<M:
-                    l[3].append(int(-r[l[1]])); l[1]+=1
-            desc=[l for l in act if l[1]<len(l[0]) and l[0][l[1]]>0]
-            if len(desc)==0 or len(desc) < thresh*32: break
-            cost += CI + fetch_cost
-            for l in desc:
-                l[2]+=1
-                if l[2]>=l[0][l[1]]: l[1]+=1; l[2]=0
-        while True:
-            pend=[l for l in act if l[3]]
-            if not pend: break
-            ms=max(l[3][0] for l in pend)
-            cost += ms*CS+CL
-            for l in pend: l[3].pop(0)
-        for i in range(32):
-            l=lanes[i]
-            if l is not None and l[1]>=len(l[0]) and not l[3]: lanes[i]=None
-        if not any(l is not None for l in lanes) and nxt>=P: break
-    return cost
-for K in (4,8,16):
-    for M in (1,2):
-        for th in (0.5,0.65,0.8):
-            run(f'spec2 M={M} thresh {th}', lambda pr: sim_spec2(pr,M,th), K, trials=100)
