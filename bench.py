@@ -322,7 +322,11 @@ def main():
         "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit, "counted_at_spp": cnt_spp,
         "ms_per_launch": mk_ms_per_launch, "launches": mk_launches,
         "kernel_share_of_step": mk_ms / dev_ms if world == 1 else None,
+        # BVH-fetch regime: algorithmic bytes/ray x rays/s.  Served from shared memory when the
+        # scene is staged there (C1/C2/C3/C5), from L1/L2 otherwise (C4: ~86 MB, L2-resident), never from HBM
         "scene_bytes_per_ray": bytes_per_ray, "scene_fetch_gbs": smem_bw,
+        "scene_in_shared_memory": bool(sc.bvh_info().in_shared_memory),
+        "scene_fetch_vs_hbm_peak": smem_bw / peaks["hbm_gbs"],
         "hbm": {"note": "HBM carries only the per-sample radiance buffer (16 B written + 16 B read per sample) "
                         "and the framebuffer; the scene is staged in shared memory",
                 "achieved": 32.0 * samples_per_rank / (ms_per_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"},
