@@ -156,9 +156,12 @@ def run_reference(args, rank, world):
 def config_dict(args, cam_opts, scene, world):
     cam_w = cam_opts.image_width
     return {"workload": f"{args.config}: {scene.name} scene, {scene.n_objects()} hittables, {cam_w} px wide, "
-                        f"{cam_opts.spp} spp/GPU, depth {cam_opts.max_depth}",
-            "spheres": int(len(scene.spheres)), "quads": int(len(scene.quads)), "width": int(cam_w), "spp_per_gpu": int(cam_opts.spp),
-            "max_depth": int(cam_opts.max_depth), "parallelism": f"sample-split x{world}" if world > 1 else "single GPU",
+                        f"{cam_opts.spp} spp{'/GPU' if args.split == 'weak' else ' in total'}, depth {cam_opts.max_depth}",
+            "spheres": int(len(scene.spheres)), "quads": int(len(scene.quads)), "width": int(cam_w),
+            "spp_per_gpu": int(cam_opts.spp) if args.split == "weak" else int(cam_opts.spp) // max(1, world),
+            "spp_total": int(cam_opts.spp) * (world if args.split == "weak" else 1),
+            "max_depth": int(cam_opts.max_depth),
+            "parallelism": f"sample-split x{world} ({args.split})" if world > 1 else "single GPU",
             "l2": "per-pass radiance buffer (512 MiB) exceeds L2; the scene is shared-memory resident by design",
             "seed": scenes.RENDER_SEED}
 
@@ -172,6 +175,9 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(scenes.CONFIGS))
     ap.add_argument("--width", type=int, default=None, help="override image width (testing)")
     ap.add_argument("--spp", type=int, default=None, help="override samples per pixel (testing)")
+    ap.add_argument("--split", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank renders the config's spp (default, per-GPU work fixed); "
+                         "strong: the config's spp is divided over the ranks (BASELINE config C5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -198,8 +204,13 @@ def main():
 
     scene_data, cam_opts = workload(args.config, args.width, args.spp)
     cam = api.camera_from_options(cam_opts)
-    W, H, spp = cam.width, cam.height, cam.spp
+    W, H = cam.width, cam.height
     n_pix = W * H
+    from raytracer_go_b200 import sharding
+    if args.split == "strong":
+        sample_offset, spp, total_spp = sharding.sample_split_strong(rank, world, cam.spp)
+    else:
+        sample_offset, spp, total_spp = sharding.sample_split_weak(rank, world, cam.spp)
     samples_per_rank = n_pix * spp
 
     sc = api.Scene(scene_data, local_rank)
@@ -208,13 +219,12 @@ def main():
     accum = torch.empty(n_pix * 3, dtype=torch.float32, device="cuda")
 
     def step():
-        st = sc.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=rank * spp,
+        st = sc.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=sample_offset,
                                     sample_count=spp)
-        if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)  # sample-split exchange step (NVLink)
+        sharding.reduce_accumulators(accum, dst=0)  # sample-split exchange step (one NCCL reduce over NVLink)
         rgb = None
         if rank == 0:
-            rgb = api.resolve_device(accum.data_ptr(), W, H, spp * world, local_rank, stream.cuda_stream)
+            rgb = api.resolve_device(accum.data_ptr(), W, H, total_spp, local_rank, stream.cuda_stream)
         return st, rgb
 
     def barrier():
@@ -252,7 +262,7 @@ def main():
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, wall_ms, rays = float(mx[0]), float(mx[1]), float(sm[2])
     ms_per_step = dev_ms / args.steps
-    total_samples = samples_per_rank * world
+    total_samples = n_pix * total_spp  # all ranks together
     value = total_samples / (ms_per_step * 1e-3) / 1e6
     mrays = rays / args.steps / (ms_per_step * 1e-3) / 1e6
 
@@ -262,7 +272,7 @@ def main():
     if not args.no_e2e:
         def e2e_step():
             with api.Scene(scene_data, local_rank) as s2:
-                rgb8, acc, _ = s2.render(cam, scenes.RENDER_SEED, sample_offset=rank * spp, sample_count=spp,
+                rgb8, acc, _ = s2.render(cam, scenes.RENDER_SEED, sample_offset=sample_offset, sample_count=spp,
                                          want_accum=world > 1)
             return rgb8
         e2e_step()
@@ -342,7 +352,7 @@ def main():
 
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.split,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mrays_s": mrays,
         "config": config_dict(args, cam_opts, scene_data, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
