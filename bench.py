@@ -323,10 +323,10 @@ def main():
         # primary_stage_kernel 1.294 GB + render_kernel<SPLIT> 1.690 GB, ncu --set full,
         # profiles/r01n_kernels_ncu_full.txt.  Algorithmic: a 16-byte radiance record per path plus a
         # 48-byte queue entry written and read once per path that survives its first segment (83 %).
-        "traffic": {"dram_bytes_per_launch": 2.984e9,
-                    "algorithmic_bytes_per_launch": 16 * 31.59e6 + 96 * 0.83 * 31.59e6,
-                    "source": "profiles/r01n_kernels_ncu_full.txt (C2 pass: 39 spp x 1200x675)"}
+        "traffic": 2.984e9
         if args.config == "C2" and not args.width else None,
+        "traffic_detail": {"unit": "bytes of DRAM traffic per pass (both kernels)", "algorithmic_bytes": 16 * 31.59e6 + 96 * 0.83 * 31.59e6,
+                           "source": "profiles/r01n_kernels_ncu_full.txt (C2 pass: 39 spp x 1200x675 = 31.59 M paths)"},
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz {peaks['sm_max_mhz']:.0f} ({peak_src} MEASURED_PEAKS.json clock)",
         "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": n_box,
         "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit, "counted_at_spp": cnt_spp,
