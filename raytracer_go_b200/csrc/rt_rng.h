@@ -57,29 +57,13 @@ struct PathRng {
 // math.go:30-32: min + r*(max-min)
 RT_HD float rand_range(float r, float lo, float hi) { return lo + r * (hi - lo); }
 
-// One trial of the cube rejection sampler (vec3.go:178-186): the candidate of a block and whether it
-// lies inside the unit ball.
-RT_HD bool unit_trial(const RngBlock &b, V3 &v) {
-    v = v3(rand_range(b.u0, -1.0f, 1.0f), rand_range(b.u1, -1.0f, 1.0f), rand_range(b.u2, -1.0f, 1.0f));
-    return lensq(v) < 1.0f;
-}
-
-// vec3.go:182-190 (NewVec3UnitRandOnUnitSphere32): cube rejection, then Unit(); one block per trial,
-// the first accepted trial wins and only the blocks up to it are consumed.  The first two trials are
-// evaluated up front by every lane (a warp runs the loop as long as its unluckiest lane: with 52 %
-// acceptance two convergent trials leave 23 % of the lanes for the loop instead of 48 %); the second
-// block is handed back when the first trial was accepted, so the stream is exactly the sequential one.
+// vec3.go:182-190 (NewVec3UnitRandOnUnitSphere32): cube rejection, then Unit(); one block per trial
 RT_HD V3 rand_unit(PathRng &rng) {
-    V3 v, v2;
-    const bool ok1 = unit_trial(rng.next(), v);
-    const bool ok2 = unit_trial(rng.next(), v2);
-    if (ok1) {
-        rng.block--; // the second block was not needed: give it back
-    } else if (ok2) {
-        v = v2;
-    } else {
-        for (;;)
-            if (unit_trial(rng.next(), v)) break;
+    V3 v;
+    for (;;) {
+        const RngBlock b = rng.next();
+        v = v3(rand_range(b.u0, -1.0f, 1.0f), rand_range(b.u1, -1.0f, 1.0f), rand_range(b.u2, -1.0f, 1.0f));
+        if (lensq(v) < 1.0f) break;
     }
     return unit(v); // after the loop: the sqrt and divide run once, with the lanes reconverged
 }
