@@ -134,8 +134,6 @@ struct rt_scene {
     int n_stages = 1;                      // coherent stages before the megakernel (RT_B200_STAGES)
     int primary_grid[2][2] = {{0, 0}, {0, 0}}; // [COUNT][FIRST]
     size_t primary_smem[2][2] = {{0, 0}, {0, 0}};
-    bool use_pool = false; // pool-variant megakernel (RT_B200_KERNEL=pool)
-    int pool_block = 512, pool_k = 4;
     // device buffers
     F4 *d_nodes = nullptr, *d_sph = nullptr, *d_mats = nullptr, *d_quads = nullptr;
     bool has_quads = false;
@@ -346,19 +344,13 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 1);
     {
         const char *kv = getenv("RT_B200_KERNEL");
-        s->use_pool = kv && std::string(kv) == "pool";
         // default: two-stage ("split"); RT_B200_KERNEL=mega selects the one-stage megakernel
         s->use_split = kv ? std::string(kv) == "split" : true;
         s->n_stages = std::min(RT_MAX_STAGES, std::max(1, env_int("RT_B200_STAGES", 1)));
-        s->pool_block = env_int("RT_B200_POOL_BLOCK", 512);
-        s->pool_k = env_int("RT_B200_POOL_K", 4);
     }
     const size_t budget = std::min<size_t>(s->smem_optin, 200 * 1024);
     s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
                   smem_total_bytes(s->dev, s->block) <= budget;
-    if (s->use_pool)
-        s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
-                      pool_smem_bytes(s->dev, s->pool_block, s->pool_k, true) <= s->smem_optin;
     return RT_OK;
 }
 
@@ -454,30 +446,6 @@ static int launch_render_b(rt_scene *s, const RenderParams &p) {
     }
 }
 
-template <int BLOCK, int K, bool SMEM, bool COUNT>
-static int launch_pool_t(rt_scene *s, const RenderParams &p) {
-    auto kern = render_pool_kernel<BLOCK, K, SMEM, COUNT>;
-    if (s->grid_cache[COUNT] == 0) {
-        const size_t smem = pool_smem_bytes(p.sc, BLOCK, K, SMEM);
-        if (smem > s->smem_optin) return fail(RT_ERR_UNSUPPORTED, "pool kernel needs %zu bytes of shared memory", smem);
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
-        if (per_sm < 1) return fail(RT_ERR_CUDA, "pool kernel does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
-        s->grid_cache[COUNT] = s->sm_count * per_sm;
-        s->smem_cache[COUNT] = smem;
-    }
-    kern<<<s->grid_cache[COUNT], BLOCK, s->smem_cache[COUNT], s->stream>>>(p);
-    CU(cudaGetLastError());
-    return RT_OK;
-}
-
-template <bool SMEM, bool COUNT>
-static int launch_pool_b(rt_scene *s, const RenderParams &p) {
-    if (s->pool_block == 768 && s->pool_k == 2) return launch_pool_t<768, 2, SMEM, COUNT>(s, p);
-    return launch_pool_t<512, 4, SMEM, COUNT>(s, p);
-}
-
 // staged mode: n_stages coherent stage kernels (segment 0 from the camera, segment k from the queue of
 // stage k-1, ping-pong buffers), then the megakernel on the survivors of the last stage
 template <bool SMEM, bool COUNT, bool QUADS>
@@ -507,7 +475,6 @@ template <bool SMEM, bool COUNT>
 static int launch_render_q(rt_scene *s, const RenderParams &p) {
     if (s->use_split) return s->has_quads ? launch_split<SMEM, COUNT, true>(s, p) : launch_split<SMEM, COUNT, false>(s, p);
     if (s->has_quads) return launch_render_b<SMEM, COUNT, true>(s, p);
-    if (s->use_pool) return launch_pool_b<SMEM, COUNT>(s, p); // experimental pool variant: spheres only
     return launch_render_b<SMEM, COUNT, false>(s, p);
 }
 

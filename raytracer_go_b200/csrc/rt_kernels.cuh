@@ -1,7 +1,7 @@
 // rt_kernels.cuh — the sm_100a kernels of librt_b200.so and the device-side scene they read.
 //
+//   primary_stage_kernel  first segment of every path, traced as coherent warps (two-stage mode, default)
 //   render_kernel       persistent megakernel: one lane = one (pixel, sample) path at a time
-//   render_pool_kernel  experimental variant (per-warp ray pool, dynamic fetch); measured slower, see DESIGN.md
 //   reduce_kernel       ordered FP32 accumulation of a pass's per-sample radiances (camera.go:255-260)
 //   resolve_kernel      1/spp, sqrt, clamp, *255.999, truncate (camera.go:261, vec3.go:141-166)
 //   add_kernel          accumulator += accumulator (multi-GPU gather)
@@ -344,237 +344,6 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
             }
         }
     }
-    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
-#pragma unroll
-    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
-        unsigned long long x = v[q];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0 && x) atomicAdd(p.stats + q, x);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// render megakernel, pool variant: each warp owns a pool of K*32 paths
-// ---------------------------------------------------------------------------------------------
-// The lock-step megakernel above keeps only ~12 of 32 lanes busy in traversal because rays of one
-// warp need very different numbers of node visits (9.5 +- 4.1, max 50).  Here a warp owns P = 32*K
-// paths.  A round is: (1) TRACE — the P rays sit in a shared-memory pool; a lane that finishes its
-// ray immediately fetches the next untraced one (dynamic fetch), so lanes stay busy until the pool
-// is drained; (2) SHADE — lane l shades its own paths l, l+32, ... (their state lives in its
-// registers), all lanes together, and regenerates finished paths from the warp's chunk of the path
-// index space.  The arithmetic of a path is the same functions in the same order as above, so the
-// image is bit-identical; only the scheduling differs.
-//
-// Pool entry of slot s (per warp): A[s] = (o.xyz, t)  B[s] = (d.xyz, bits(hit slot | RT_POOL_DEAD)).
-#define RT_POOL_DEAD 0xFFFFFFFEu
-
-static size_t pool_smem_bytes(const DevScene &s, int block, int K, bool scene_in_smem) {
-    size_t b = scene_in_smem ? scene_smem_bytes(s) + ((s.n_slots & 1) ? 8 : 0) : 0;
-    b += (size_t)(scene_in_smem ? s.stack_depth : 0) * block * 4; // traversal stacks
-    b = (b + 15) & ~(size_t)15;
-    return b + (size_t)block * K * 32; // pool: 2 x float4 per path
-}
-
-template <int BLOCK, int K, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(BLOCK, 1) render_pool_kernel(const __grid_constant__ RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr uint32_t P = 32u * K;
-    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats;
-    const I2 *meta = p.sc.meta;
-    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
-    Stack stack;
-    size_t used = 0;
-    if constexpr (SMEM) {
-        SmemScene s = stage_scene(p.sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, mats = s.mats, meta = s.meta;
-        stack.base = s.stack + threadIdx.x;
-        stack.stride = BLOCK;
-        used = (size_t)((unsigned char *)(s.stack + (size_t)p.sc.stack_depth * BLOCK) - smem_raw);
-        used = (used + 15) & ~(size_t)15;
-    }
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    float4 *poolA = reinterpret_cast<float4 *>(smem_raw + used) + (size_t)warp * 2 * P;
-    float4 *poolB = poolA + P;
-
-    // ---- per-lane state of the K paths this lane owns (slot = 32*k + lane) ----
-    V3 thr[K], rad[K];
-    uint32_t idx[K], blk[K]; // path index in the pass; next Philox block of the path's stream
-    int depth[K];
-    uint32_t alive = 0; // bit k: path k is in flight
-    uint32_t warp_next = 0, warp_end = 0;
-    bool exhausted = false;
-    unsigned long long n_rays = 0, n_hits = 0;
-    WorkCounters wc;
-    wc.box_tests = wc.sphere_tests = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        thr[k] = v3(1, 1, 1), rad[k] = v3(0, 0, 0), idx[k] = 0, blk[k] = 0, depth[k] = 0;
-        poolB[32 * k + lane] = make_float4(0, 0, 0, __uint_as_float(RT_POOL_DEAD));
-    }
-
-    // Regenerate path k of every lane that has none (camera.go:265-299), from the warp's chunk.
-    auto regenerate = [&](int k) {
-        const unsigned need = __ballot_sync(0xffffffffu, !((alive >> k) & 1u));
-        if (!need) return;
-        if (warp_next >= warp_end && !exhausted) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= p.total_paths) exhausted = true;
-            else warp_next = base, warp_end = min(base + RT_CHUNK, p.total_paths);
-        }
-        const uint32_t avail = warp_end - warp_next;
-        const uint32_t rank = __popc(need & lt_mask);
-        if (!((alive >> k) & 1u) && rank < avail) {
-            const uint32_t id = warp_next + rank;
-            const uint32_t pp = id / p.spp_pass, ks = id - pp * p.spp_pass;
-            const uint32_t pixel = p.pixel_begin + pp;
-            const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
-            PathRng rng;
-            rng.init(p.seed, pixel, p.sample_begin + ks);
-            V3 o, d;
-            generate_ray(p.cam, rng, i, j, o, d);
-            idx[k] = id, blk[k] = rng.block, depth[k] = 0;
-            thr[k] = v3(1, 1, 1), rad[k] = v3(0, 0, 0);
-            poolA[32 * k + lane] = make_float4(o.x, o.y, o.z, 0.0f);
-            poolB[32 * k + lane] = make_float4(d.x, d.y, d.z, 0.0f);
-            alive |= 1u << k;
-        }
-        warp_next += min(avail, (uint32_t)__popc(need));
-    };
-
-#pragma unroll
-    for (int k = 0; k < K; k++) regenerate(k);
-    __syncwarp();
-
-    while (__ballot_sync(0xffffffffu, alive != 0) != 0) {
-        // ================= TRACE: drain the pool with dynamic fetch =================
-        {
-            uint32_t cursor = 0; // warp-uniform: next untraced slot
-            bool has_ray = false;
-            uint32_t cur = 0, ref = RT_REF_NONE, best = RT_REF_NONE;
-            V3 o = v3(0, 0, 0), d = v3(0, 0, 0), inv = v3(0, 0, 0), noi = v3(0, 0, 0);
-            float a = 0, tbest = 0;
-            for (;;) {
-                const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
-                if (idle != 0 && cursor < P) {
-                    const uint32_t my = cursor + __popc(idle & lt_mask);
-                    if (!has_ray && my < P) {
-                        const float4 B = poolB[my];
-                        if (__float_as_uint(B.w) != RT_POOL_DEAD) {
-                            const float4 A = poolA[my];
-                            o = v3(A.x, A.y, A.z), d = v3(B.x, B.y, B.z);
-                            inv = v3(cull_rcp(d.x), cull_rcp(d.y), cull_rcp(d.z));
-                            noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-                            a = lensq(d);
-                            tbest = INFINITY, best = RT_REF_NONE, ref = p.sc.root_ref;
-                            stack.reset();
-                            cur = my, has_ray = true;
-                            n_rays++;
-                        }
-                    }
-                    cursor = min(P, cursor + (uint32_t)__popc(idle));
-                }
-                if (__ballot_sync(0xffffffffu, has_ray) == 0) {
-                    if (cursor >= P) break;
-                    continue;
-                }
-                if (has_ray) {
-                    // descend through inner nodes until this lane holds a leaf (or nothing)
-                    while (!(ref & RT_LEAF)) {
-                        const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1];
-                        const F4 r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
-                        float tl, tr;
-                        const bool hl = box_test(l0, l1, inv, noi, 0.001f, tbest, tl);
-                        const bool hr = box_test(r0, r1, inv, noi, 0.001f, tbest, tr);
-                        if (COUNT) wc.box_tests += 2;
-                        const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
-                        if (hl && hr) {
-                            const bool left_first = tl <= tr;
-                            stack.push(left_first ? rref : lref);
-                            ref = left_first ? lref : rref;
-                        } else if (hl) {
-                            ref = lref;
-                        } else if (hr) {
-                            ref = rref;
-                        } else {
-                            ref = stack.pop();
-                        }
-                    }
-                    if (ref != RT_REF_NONE) {
-                        const uint32_t first = (ref & ~RT_LEAF) >> 3, count = (ref & 7u) + 1;
-                        for (uint32_t s = first; s < first + count; s++) {
-                            const F4 sp = sph[s];
-                            float t;
-                            if (COUNT) wc.sphere_tests += 1;
-                            if (!sphere_candidate(sp, o, d, a, 0.001f, t)) continue;
-                            if (t < tbest) {
-                                tbest = t, best = s;
-                            } else if (t == tbest && best != RT_REF_NONE) {
-                                if (meta[s].x < meta[best].x) best = s; // exact tie: earlier object wins
-                            }
-                        }
-                        ref = stack.pop();
-                    }
-                    if (ref == RT_REF_NONE) { // traversal finished: publish (t, hit slot) in the pool
-                        poolA[cur].w = tbest;
-                        poolB[cur].w = __uint_as_float(best);
-                        has_ray = false;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        // ================= SHADE: every lane advances its own K paths =================
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const uint32_t slot = 32u * k + lane;
-            if ((alive >> k) & 1u) {
-                const float4 A = poolA[slot], B = poolB[slot];
-                V3 o = v3(A.x, A.y, A.z), d = v3(B.x, B.y, B.z);
-                const uint32_t hs = __float_as_uint(B.w);
-                bool done;
-                if (hs == RT_REF_NONE) {
-                    rad[k] = rad[k] + thr[k] * p.cam.background; // ray.go:53
-                    done = true;
-                } else {
-                    n_hits++;
-                    const F4 s = sph[hs];
-                    const int mi = meta[hs].y;
-                    const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
-                    const uint32_t pp = idx[k] / p.spp_pass, ks = idx[k] - pp * p.spp_pass;
-                    PathRng rng;
-                    rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + ks);
-                    rng.block = blk[k];
-                    V3 atten, emitted;
-                    const bool scattered = shade_hit(m0, m1, p.sc.tex, s, A.w, rng, o, d, atten, emitted);
-                    blk[k] = rng.block;
-                    rad[k] = rad[k] + thr[k] * emitted; // ray.go:41,50
-                    if (!scattered) {
-                        done = true; // ray.go:44-46
-                    } else {
-                        thr[k] = thr[k] * atten; // ray.go:48
-                        depth[k]++;
-                        done = depth[k] >= p.cam.max_depth; // ray.go:33-35
-                    }
-                }
-                if (done) {
-                    p.samples[idx[k]] = make_float4(rad[k].x, rad[k].y, rad[k].z, 0.0f);
-                    alive &= ~(1u << k);
-                    poolB[slot].w = __uint_as_float(RT_POOL_DEAD);
-                } else {
-                    poolA[slot] = make_float4(o.x, o.y, o.z, 0.0f);
-                    poolB[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-                }
-            }
-            regenerate(k);
-        }
-        __syncwarp();
-    }
-
     unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
 #pragma unroll
     for (int q = 0; q < (COUNT ? 4 : 2); q++) {
