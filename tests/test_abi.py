@@ -88,3 +88,18 @@ def test_camera_from_options_equals_oracle(rtlib, orc):
         a, b = abi.rt_camera(), orc.camera_from_options(o)
         assert rtlib.rt_camera_from_options(C.byref(o), C.byref(a)) == 0
         assert bytes(a) == bytes(b)
+
+
+def test_non_finite_geometry_is_rejected(rtlib):
+    """Validation happens before any device work, so it is checkable without a GPU."""
+    bad = scenes.random_scene()
+    bad.spheres["cx"][7] = np.inf
+    desc, keep = bad.to_desc()
+    h = C.c_void_p()
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_INVALID_ARGUMENT
+    assert b"non-finite" in rtlib.rt_last_error()
+    m = scenes.mixed_scene()
+    m.quad_ids = np.array([0, 2, 3, 3], np.uint32)        # not a permutation
+    desc, keep = m.to_desc()
+    rc = rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h))
+    assert rc in (abi.RT_ERR_INVALID_ARGUMENT, abi.RT_ERR_NO_DEVICE)   # the id check needs the device selected first

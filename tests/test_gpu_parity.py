@@ -387,3 +387,20 @@ def test_binary_ppm_equals_text_ppm(gpu):
     raw = b.getvalue()
     assert raw.startswith(b"P6\n96 54\n255\n")
     assert np.array_equal(np.frombuffer(raw[len(b"P6\n96 54\n255\n"):], np.uint8), text)
+
+
+def test_negative_and_zero_radius_spheres(gpu, orc):
+    """Hollow glass (negative radius flips the normal, hittables.go:119) and a zero-radius sphere."""
+    from tests.test_hostsim import _hollow_glass_scene
+    s = _hollow_glass_scene()
+    cam = api.camera_from_options(scenes.camera_options(200, 8, look_from=(-2, 2, 1), look_at=(0, 0, -1), vfov_deg=40,
+                                                        defocus_deg=0.0, focus_dist=1.0))
+    with api.Scene(s) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+        ro, rd = orc.primary_rays(cam, SEED, 0, cam.width * cam.height, 0, 1)
+        ids, ts = sc.trace(ro, rd)
+    rids, rts = orc.trace(s, ro, rd)
+    assert np.array_equal(ids, rids) and (rids == 1).any() and not (rids == 4).any()
+    rrgb, racc, rst = orc.render(s, cam, SEED, order=orc.ORDER_ITERATIVE)
+    assert (acc.view(np.uint32) == racc.view(np.uint32)).all(-1).mean() > 0.9995
+    assert (rgb != rrgb).any(-1).mean() < 1e-3 and abs(int(st.rays) - int(rst.rays)) <= 1e-4 * rst.rays

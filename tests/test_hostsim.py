@@ -191,3 +191,41 @@ def test_noise_texture_scenes_equal_oracle(hs, orc, name):
     assert np.array_equal(acc.view(np.uint32), racc.view(np.uint32))
     assert np.array_equal(rgb, rrgb)
     assert len(np.unique(rgb.reshape(-1, 3), axis=0)) > 50   # marble, not a flat colour
+
+
+def _hollow_glass_scene():
+    """The book's hollow glass sphere: a dielectric sphere with NEGATIVE radius inside a positive one
+    (hittables.go:119: the normal is (p - c) * r, so a negative radius flips it)."""
+    tex = np.zeros(2, scenes.TEXTURE_DT)
+    tex[0]["kind"], tex[0]["a"], tex[0]["b"], tex[0]["scale"] = abi.RT_TEX_CHECKER, (.2, .3, .1), (.9, .9, .9), 0.32
+    tex[1]["a"] = (0.1, 0.2, 0.5)
+    mat = np.zeros(3, scenes.MATERIAL_DT)
+    mat[0]["kind"], mat[0]["texture"] = abi.RT_MAT_LAMBERTIAN, 0
+    mat[1]["kind"], mat[1]["ior"] = abi.RT_MAT_DIELECTRIC, 1.5
+    mat[2]["kind"], mat[2]["texture"] = abi.RT_MAT_LAMBERTIAN, 1
+    sph = np.zeros(5, scenes.SPHERE_DT)
+    sph[0] = (0, -100.5, -1, 100, 0)
+    sph[1] = (-1, 0, -1, 0.5, 1)
+    sph[2] = (-1, 0, -1, -0.4, 1)     # negative radius: the inner surface of the shell
+    sph[3] = (0, 0, -1, 0.5, 2)
+    sph[4] = (1, 0, -1, 0.0, 2)       # zero radius: never hit
+    return scenes.SceneData(sph, mat, tex, name="hollow-glass")
+
+
+def test_negative_and_zero_radius_spheres(hs, orc):
+    s = _hollow_glass_scene()
+    cam = orc.camera_from_options(scenes.camera_options(96, 6, look_from=(-2, 2, 1), look_at=(0, 0, -1), vfov_deg=40,
+                                                        defocus_deg=0.0, focus_dist=1.0))
+    ro, rd = orc.primary_rays(cam, 3, 0, cam.width * cam.height, 0, 2)
+    ids, ts, _, _ = hs_trace(hs, s, ro, rd)
+    rids, rts = orc.trace(s, ro, rd)
+    assert np.array_equal(ids, rids) and np.array_equal(ts[rids >= 0], rts[rids >= 0])
+    assert (rids == 1).any() and not (rids == 4).any()
+    inside_o = np.tile(np.array([[-1, 0, -1]], np.float32), (64, 1))          # from inside the shell
+    inside_d = np.random.default_rng(1).normal(size=(64, 3)).astype(np.float32)
+    i2, t2, _, _ = hs_trace(hs, s, inside_o, inside_d)
+    r2, rt2 = orc.trace(s, inside_o, inside_d)
+    assert np.array_equal(i2, r2) and (r2 == 2).all() and np.array_equal(t2, rt2)
+    rgb, acc = _hs_render(hs, s, cam, 9, cam.spp)
+    rrgb, racc, _ = orc.render(s, cam, 9, order=orc.ORDER_ITERATIVE)
+    assert np.array_equal(acc.view(np.uint32), racc.view(np.uint32)) and np.array_equal(rgb, rrgb)
