@@ -115,10 +115,11 @@ typedef struct rt_scene_desc {
     uint32_t n_textures;
     const rt_image *images;
     uint32_t n_images;
-    /* Radius (world units) around the scene within which ray origins are expected; used only to
-     * size the conservative padding of the device BVH boxes so that box culling can never drop a
-     * sphere the reference's float32 Sphere.Hit (hittables.go:96-116) would accept.  0 = derive
-     * from the sphere set. */
+    /* Sizes the conservative padding of the device BVH boxes: box culling never drops a primitive the
+     * reference's float32 Hit would accept for any ray that starts within this distance (world units)
+     * of the surface it hits.  0 = derive from the scene and enlarge as needed to cover the camera or
+     * an rt_trace batch (always exact); > 0 = a fixed envelope (use it for scenes much larger than the
+     * distances at which float32 sphere tests are still meaningful). */
     float ray_origin_radius;
     /* Quads (Quad/Box, hittables.go:138-216).  Object IDs: the position of a
      * hittable in World.hittables (hittables.go:48-53), which World.Hit breaks exact ties by.  When

@@ -8,12 +8,13 @@
 // error of at most ~20 u |d|^2 |o-c|^2, so the reference can accept a root for a ray that
 // geometrically passes up to  delta = 20 u |o-c|^2 / (2 r)  outside the sphere; the accepted
 // point then lies within r + delta of the centre.  Each sphere's box is therefore grown by
-//   pad = K u D^2 / (2 r) + 8 u (D + |m| + |c| + r),   K = 24,
-// where D bounds |o - c| for every ray origin o within `origin_radius` of the scene's median
-// centre m (the second term covers the fused slab test's own rounding).  A quad's accepted point
+//   pad = K u D^2 / (2 r) + 8 u (D + |m| + |c| + r),   K = 24,   D = r + origin_radius,
+// i.e. for every ray that starts within `origin_radius` of the surface it hits (the second term
+// covers the fused slab test's own rounding; m = median centre of the scene).  A quad's accepted point
 // is within a few ulp of its plane and of its edges: its box (the reference's padded box,
-// hittables.go:161 / bvh.go:63-82) is grown by 32 u (D + |Q| + |u| + |v|).  rt_render / rt_trace
-// enlarge origin_radius (refit, no rebuild) when a camera or a ray batch lies outside it.
+// hittables.go:161 / bvh.go:63-82) is grown by 32 u (D + |Q| + |u| + |v|).  When the radius is derived
+// (rt_scene_desc.ray_origin_radius = 0), rt_render / rt_trace enlarge it (refit, no rebuild) so that
+// it covers the camera or the ray batch; an explicit radius is a fixed envelope.
 #include "bvh_build.h"
 #include "rt_shade.h"
 
@@ -65,12 +66,11 @@ void prim_center(const ScenePrims &p, uint32_t g, double c[3], double *extent) {
     }
 }
 
-// Padded box of one primitive for ray origins within origin_radius of m.
+// Padded box of one primitive for rays that start within origin_radius of its surface.
 Box padded_box(const ScenePrims &p, uint32_t g, const double m[3], double origin_radius, float *pad_out) {
     double c[3], ext;
     prim_center(p, g, c, &ext);
-    const double dx = c[0] - m[0], dy = c[1] - m[1], dz = c[2] - m[2];
-    const double D = origin_radius + std::sqrt(dx * dx + dy * dy + dz * dz);
+    const double D = origin_radius + ext; // bound on |o - c| (ext = radius, or a quad's half diagonal)
     const double cmax = std::max(std::fabs(c[0]), std::max(std::fabs(c[1]), std::fabs(c[2])));
     const double mmax = std::max(std::fabs(m[0]), std::max(std::fabs(m[1]), std::fabs(m[2])));
     Box b;
@@ -270,8 +270,9 @@ bool load_scene_prims(const rt_scene_desc *d, ScenePrims *out) {
     return true;
 }
 
-void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90) {
+void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90, double *surface_extent) {
     m[0] = m[1] = m[2] = 0, *extent90 = 0;
+    if (surface_extent) *surface_extent = 0;
     const size_t n = prims.size();
     if (n == 0) return;
     std::vector<float> v(n);
@@ -284,7 +285,10 @@ void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90
     }
     for (size_t g = 0; g < n; g++) {
         double dx = c[3 * g] - m[0], dy = c[3 * g + 1] - m[1], dz = c[3 * g + 2] - m[2];
-        v[g] = (float)(std::sqrt(dx * dx + dy * dy + dz * dz) + ext[g]);
+        const double dc = std::sqrt(dx * dx + dy * dy + dz * dz);
+        v[g] = (float)(dc + ext[g]);
+        // how far from m the nearest point of the farthest primitive can be
+        if (surface_extent) *surface_extent = std::max(*surface_extent, dc - ext[g]);
     }
     size_t k90 = (size_t)((n - 1) * 0.9);
     std::nth_element(v.begin(), v.begin() + k90, v.end());

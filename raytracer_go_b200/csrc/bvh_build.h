@@ -33,8 +33,10 @@ struct FlatBvh {
 void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out);
 // Recompute all boxes for a (larger) origin radius; topology and slot order are unchanged.
 void refit_flat_bvh(const ScenePrims &prims, float origin_radius, FlatBvh *bvh);
-// Per-axis median of the primitive centres and the 90th percentile of |c - m| + extent.
-void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90);
+// Per-axis median m of the primitive centres, the 90th percentile of |c - m| + extent, and
+// (optional) max over primitives of |c - m| - extent: how far from m the nearest point of the farthest
+// primitive is.
+void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90, double *surface_extent = nullptr);
 // Fold each material's texture into its 32-byte device record (layout in rt_shade.h).
 void pack_materials(const rt_scene_desc *d, std::vector<F4> *out);
 // Copies (and validates the IDs of) the hittables of a scene description; false = bad IDs.

@@ -124,7 +124,9 @@ struct rt_scene {
     FlatBvh bvh;
     double center[3] = {0, 0, 0};
     double extent90 = 0;
-    float origin_radius = 0;
+    double surface_extent = 0; // max over primitives of (distance of its nearest point from the centre)
+    float origin_radius = 0;   // rays are exact when they start within this distance of the surface they hit
+    bool fixed_radius = false; // the caller gave ray_origin_radius: an envelope, never enlarged
     DevScene dev{};
     bool use_smem = false;
     int block = 256;
@@ -264,8 +266,9 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     if (!load_scene_prims(desc, &s->prims))
         return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
     s->has_quads = !s->prims.quads.empty();
-    compute_scene_center(s->prims, s->center, &s->extent90);
-    s->origin_radius = desc->ray_origin_radius > 0 ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
+    compute_scene_center(s->prims, s->center, &s->extent90, &s->surface_extent);
+    s->fixed_radius = desc->ray_origin_radius > 0;
+    s->origin_radius = s->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
     build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh);
 
     std::vector<F4> mats;
@@ -382,8 +385,11 @@ extern "C" int rt_scene_set_stream(rt_scene *scene, void *cuda_stream) {
 }
 
 // Grow the BVH padding when ray origins lie outside the radius it was built for.
-static int ensure_origin_radius(rt_scene *s, double needed) {
-    if (needed <= s->origin_radius || s->prims.size() == 0) return RT_OK;
+// `origin_dist` = largest distance of a ray origin from the scene centre; a ray from there can hit a
+// primitive whose nearest point is origin_dist + surface_extent away.
+static int ensure_origin_radius(rt_scene *s, double origin_dist) {
+    const double needed = origin_dist + s->surface_extent;
+    if (s->fixed_radius || needed <= s->origin_radius || s->prims.size() == 0) return RT_OK;
     s->origin_radius = (float)(needed * 1.25);
     refit_flat_bvh(s->prims, s->origin_radius, &s->bvh);
     int rc = upload_nodes(s);

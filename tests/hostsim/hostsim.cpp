@@ -25,8 +25,10 @@ struct HostScene {
 void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *s) {
     double m[3], ext;
     load_scene_prims(d, &s->prims);
-    compute_scene_center(s->prims, m, &ext);
-    float R = origin_radius > 0 ? origin_radius : (d->ray_origin_radius > 0 ? d->ray_origin_radius : (float)(2 * ext));
+    double surf;
+    compute_scene_center(s->prims, m, &ext, &surf);
+    // derived radius as rt_scene_create + a camera / ray batch anywhere within the scene's extent
+    float R = origin_radius > 0 ? origin_radius : (d->ray_origin_radius > 0 ? d->ray_origin_radius : (float)(2 * ext + surf));
     build_flat_bvh(s->prims, R, max_leaf, &s->bvh);
     pack_materials(d, &s->mats);
     s->images.resize(d->n_images);
