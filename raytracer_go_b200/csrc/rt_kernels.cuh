@@ -95,6 +95,7 @@ struct RenderParams {
     unsigned int *counter; // next unclaimed path index
     unsigned long long *stats; // rays, hits, box tests, sphere tests
     uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
+    uint32_t chunk;        // work items a warp claims per atomic (RT_CHUNK by default)
     // two-stage mode (primary_stage_kernel + render_kernel<SPLIT>): paths that survive their first
     // segment, as three float4 arrays of capacity total_paths
     float4 *queue_o;           // (o.xyz, bits path index)
@@ -152,13 +153,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
         if (dead == 0xffffffffu || (uint32_t)__popc(dead) >= p.regen_min) {
             if (warp_next >= warp_end && !exhausted) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(p.counter, RT_CHUNK);
+                if (lane == 0) base = atomicAdd(p.counter, p.chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (base >= total_items) {
                     exhausted = true;
                 } else {
                     warp_next = base;
-                    warp_end = min(base + RT_CHUNK, total_items);
+                    warp_end = min(base + p.chunk, total_items);
                 }
             }
             const uint32_t avail = warp_end - warp_next;
