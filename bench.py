@@ -162,7 +162,7 @@ def config_dict(args, cam_opts, scene, world):
             "spp_total": int(cam_opts.spp) * (world if args.split == "weak" else 1),
             "max_depth": int(cam_opts.max_depth),
             "parallelism": f"sample-split x{world} ({args.split})" if world > 1 else "single GPU",
-            "l2": "per-pass radiance buffer (512 MiB) exceeds L2; the scene is shared-memory resident by design",
+            "l2": "per-pass radiance buffer (up to 1 GiB) and survivor queue exceed L2; the scene is shared-memory resident by design",
             "seed": scenes.RENDER_SEED}
 
 

@@ -56,7 +56,7 @@ static int fail(int code, const char *fmt, ...) {
 // ---------------------------------------------------------------------------------------------
 // host side: per-device workspace, shared by all scene handles of the process
 // ---------------------------------------------------------------------------------------------
-// The per-pass radiance buffer (up to 512 MiB), the accumulator, the RGB8 image and its pinned
+// The per-pass radiance buffer (up to 1 GiB), the accumulator, the RGB8 image and its pinned
 // staging copy are cached per device for the life of the process (rt_workspace_release frees
 // them): a Camera.Render-style call creates and destroys a scene handle every time, and paying a
 // half-gigabyte cudaMalloc/cudaFree per call costs more than the render itself.  The mutex is held
