@@ -156,12 +156,14 @@ def run_reference(args, rank, world):
 def config_dict(args, cam_opts, scene, world):
     cam_w = cam_opts.image_width
     return {"workload": f"{args.config}: {scene.name} scene, {scene.n_objects()} hittables, {cam_w} px wide, "
-                        f"{cam_opts.spp} spp{'/GPU' if args.split == 'weak' else ' in total'}, depth {cam_opts.max_depth}",
+                        f"{cam_opts.spp} spp{' in total' if args.split == 'strong' else '/GPU'}, depth {cam_opts.max_depth}",
             "spheres": int(len(scene.spheres)), "quads": int(len(scene.quads)), "width": int(cam_w),
-            "spp_per_gpu": int(cam_opts.spp) if args.split == "weak" else int(cam_opts.spp) // max(1, world),
-            "spp_total": int(cam_opts.spp) * (world if args.split == "weak" else 1),
+            "spp_per_gpu": int(cam_opts.spp) // max(1, world) if args.split == "strong" else int(cam_opts.spp),
+            "spp_total": int(cam_opts.spp) * (1 if args.split == "strong" else world),
             "max_depth": int(cam_opts.max_depth),
-            "parallelism": f"sample-split x{world} ({args.split})" if world > 1 else "single GPU",
+            "parallelism": "single GPU" if world == 1 else
+                           (f"tile-split x{world}: interleaved scanlines at all {int(cam_opts.spp) * world} spp, one gather"
+                            if args.split == "tile" else f"sample-split x{world} ({args.split})"),
             "l2": "per-pass radiance buffer (up to 1 GiB) and survivor queue exceed L2; the scene is shared-memory resident by design",
             "seed": scenes.RENDER_SEED}
 
@@ -175,9 +177,10 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(scenes.CONFIGS))
     ap.add_argument("--width", type=int, default=None, help="override image width (testing)")
     ap.add_argument("--spp", type=int, default=None, help="override samples per pixel (testing)")
-    ap.add_argument("--split", default="weak", choices=["weak", "strong"],
+    ap.add_argument("--split", default="weak", choices=["weak", "strong", "tile"],
                     help="weak: every rank renders the config's spp (default, per-GPU work fixed); "
-                         "strong: the config's spp is divided over the ranks (BASELINE config C5)")
+                         "strong: the config's spp is divided over the ranks (BASELINE config C5); "
+                         "tile: interleaved scanlines at world*spp samples (weak scaling, no reduction)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -207,24 +210,34 @@ def main():
     W, H = cam.width, cam.height
     n_pix = W * H
     from raytracer_go_b200 import sharding
+    rows = None
     if args.split == "strong":
         sample_offset, spp, total_spp = sharding.sample_split_strong(rank, world, cam.spp)
+    elif args.split == "tile":
+        # interleaved scanlines, every rank renders all world*spp samples of its rows (weak scaling:
+        # the per-GPU work is that of the 1-GPU run); no reduction, one gather of the rows
+        sample_offset, spp, total_spp = 0, world * cam.spp, world * cam.spp
+        rows = sharding.row_split(rank, world, H)
     else:
         sample_offset, spp, total_spp = sharding.sample_split_weak(rank, world, cam.spp)
-    samples_per_rank = n_pix * spp
 
     sc = api.Scene(scene_data, local_rank)
     stream = torch.cuda.current_stream()
     sc.set_stream(stream.cuda_stream)
-    accum = torch.empty(n_pix * 3, dtype=torch.float32, device="cuda")
+    my_rows = rows[1] if rows else H
+    samples_per_rank = my_rows * W * spp
+    accum = torch.empty(my_rows * W * 3, dtype=torch.float32, device="cuda")
 
     def step():
         st = sc.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=sample_offset,
-                                    sample_count=spp)
-        sharding.reduce_accumulators(accum, dst=0)  # sample-split exchange step (one NCCL reduce over NVLink)
+                                    sample_count=spp, rows=rows)
+        if rows:
+            full = sharding.gather_rows(accum.view(my_rows, W, 3), H, dst=0)  # tile-split exchange: one NCCL gather
+        else:
+            full = sharding.reduce_accumulators(accum, dst=0)  # sample-split exchange: one NCCL reduce over NVLink
         rgb = None
         if rank == 0:
-            rgb = api.resolve_device(accum.data_ptr(), W, H, total_spp, local_rank, stream.cuda_stream)
+            rgb = api.resolve_device(full.data_ptr(), W, H, total_spp, local_rank, stream.cuda_stream)
         return st, rgb
 
     def barrier():
@@ -273,7 +286,7 @@ def main():
         def e2e_step():
             with api.Scene(scene_data, local_rank) as s2:
                 rgb8, acc, _ = s2.render(cam, scenes.RENDER_SEED, sample_offset=sample_offset, sample_count=spp,
-                                         want_accum=world > 1)
+                                         want_accum=world > 1 and not rows, rows=rows)
             return rgb8
         e2e_step()
         barrier()
@@ -287,7 +300,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         h2d = scene_data.nbytes() + 256
-        d2h = n_pix * 3 + (n_pix * 12 if world > 1 else 0)
+        d2h = my_rows * W * 3 + (n_pix * 12 if world > 1 and not rows else 0)
         e2e = {"value": total_samples / float(t[0]) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t[0]) * 1e3,
                "what": "rt_scene_create (host BVH build + upload) + rt_render (RGB8 to host) + rt_scene_destroy per step"}
@@ -301,7 +314,7 @@ def main():
     # at a reduced spp (per-ray statistics do not depend on spp) ----
     cnt_spp = max(1, min(spp, 4))
     stc = sc.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=0, sample_count=cnt_spp,
-                                 flags=1)
+                                 flags=1, rows=rows)
     n_box = stc.box_tests / stc.rays
     n_sph = stc.sphere_tests / stc.rays
     n_hit = stc.hits / stc.rays
@@ -352,7 +365,8 @@ def main():
 
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.split,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if args.split == "strong" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mrays_s": mrays,
         "config": config_dict(args, cam_opts, scene_data, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

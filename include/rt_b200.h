@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 3
+#define RT_B200_ABI_VERSION 4
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -171,10 +171,24 @@ typedef struct rt_render_opts {
     int32_t sample_offset; /* first global sample index rendered by this call (sample-split)      */
     int32_t sample_count;  /* samples per pixel rendered by this call; 0 = camera.spp             */
     int32_t flags;         /* RT_FLAG_*                                                           */
+    /* Row set (tile-split): this call renders only the scanlines
+     * row_begin + k*row_step, k in [0, row_count).  row_count == 0 = the whole image (row_begin and
+     * row_step are then ignored).  Every output buffer of the call (rgb_out, accum_out, d_accum) is
+     * COMPACT: row_count rows of `width` pixels, in increasing k.  Pixels keep the Philox stream of
+     * their position in the full image, so a row set is bit-identical to the same rows of the
+     * full render.  row_step > 1 interleaves the devices' rows (sky rows are cheap, ground rows
+     * are not: contiguous bands would not balance). */
+    int32_t row_begin;
+    int32_t row_count;
+    int32_t row_step;
+    int32_t reserved;
 } rt_render_opts;
 
 #define RT_FLAG_NONE 0
 #define RT_FLAG_COUNT_WORK 1 /* also fill the algorithmic-work counters of rt_stats (slower) */
+#define RT_FLAG_TILE_SPLIT 2 /* rt_render_multi: split by interleaved scanlines instead of by samples:
+                                no accumulator exchange, and the image is bit-identical to the
+                                single-GPU render */
 
 typedef struct rt_stats {
     uint64_t samples;      /* (pixel, sample) paths, camera.go:256-260                   */
@@ -225,7 +239,9 @@ int rt_render(rt_scene *scene, const rt_camera *camera, const rt_render_opts *op
  * program): sample-split.  Device k of `devices` renders its share of the samples on
  * its own host thread; the FP32 accumulators are peer-copied to devices[0], added in device order
  * and resolved there.  Takes the scene description (a scene handle lives on one device).  Every
- * (pixel, sample) keeps its single-GPU Philox stream; only the FP32 summation order differs. */
+ * (pixel, sample) keeps its single-GPU Philox stream; only the FP32 summation order differs.
+ * With RT_FLAG_TILE_SPLIT the devices take interleaved scanlines (device k: rows k, k+n, ...) at all
+ * samples instead and resolve them themselves: no exchange, image bit-identical to rt_render. */
 int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
                     const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
                     rt_stats *stats);

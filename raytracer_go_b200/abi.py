@@ -5,7 +5,7 @@ sizes/offsets against the compiled library's view where that is observable.
 """
 import ctypes as C
 
-RT_B200_ABI_VERSION = 3
+RT_B200_ABI_VERSION = 4
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1
@@ -19,6 +19,7 @@ RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = 0, 1, 2, 3
 
 RT_FLAG_NONE = 0
 RT_FLAG_COUNT_WORK = 1
+RT_FLAG_TILE_SPLIT = 2
 
 _f3 = C.c_float * 3
 
@@ -79,7 +80,8 @@ class rt_camera_options(C.Structure):
 
 class rt_render_opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("device", C.c_int32), ("sample_offset", C.c_int32),
-                ("sample_count", C.c_int32), ("flags", C.c_int32)]
+                ("sample_count", C.c_int32), ("flags", C.c_int32), ("row_begin", C.c_int32),
+                ("row_count", C.c_int32), ("row_step", C.c_int32), ("reserved", C.c_int32)]
 
 
 class rt_stats(C.Structure):

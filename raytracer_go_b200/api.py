@@ -53,21 +53,27 @@ class Scene:
         """Run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0 restores."""
         lib.check(self._lib.rt_scene_set_stream(self._h, C.c_void_p(cuda_stream)))
 
-    def render(self, cam, seed=scenes.RENDER_SEED, sample_offset=0, sample_count=0, want_accum=False, flags=0):
-        """rt_render -> (rgb (H,W,3) uint8, accum (H,W,3) float32 or None, rt_stats)."""
-        H, W = cam.height, cam.width
+    def render(self, cam, seed=scenes.RENDER_SEED, sample_offset=0, sample_count=0, want_accum=False, flags=0,
+               rows=None):
+        """rt_render -> (rgb (H,W,3) uint8, accum (H,W,3) float32 or None, rt_stats).  `rows` =
+        (row_begin, row_count, row_step) renders only those scanlines; the outputs then have row_count rows."""
+        if rows and rows[1] == 0:  # in the C struct row_count 0 means "the whole image"
+            raise ValueError("empty row set")
+        H, W = (rows[1] if rows else cam.height), cam.width
         rgb = np.empty((H, W, 3), np.uint8)
         acc = np.empty((H, W, 3), np.float32) if want_accum else None
-        opts = abi.rt_render_opts(seed, self.device, sample_offset, sample_count, flags)
+        opts = abi.rt_render_opts(seed, self.device, sample_offset, sample_count, flags, *(rows or (0, 0, 0)))
         st = abi.rt_stats()
         lib.check(self._lib.rt_render(self._h, C.byref(cam), C.byref(opts), rgb.ctypes.data_as(C.c_void_p),
                                       acc.ctypes.data_as(C.c_void_p) if want_accum else None, C.byref(st)))
         return rgb, acc, st
 
     def render_accum_device(self, cam, d_accum_ptr, seed=scenes.RENDER_SEED, sample_offset=0, sample_count=0,
-                            flags=0):
-        """rt_render_accum_device into a device buffer of W*H*3 float32 (e.g. tensor.data_ptr())."""
-        opts = abi.rt_render_opts(seed, self.device, sample_offset, sample_count, flags)
+                            flags=0, rows=None):
+        """rt_render_accum_device into a device buffer of rows*W*3 float32 (e.g. tensor.data_ptr())."""
+        if rows and rows[1] == 0:
+            raise ValueError("empty row set")
+        opts = abi.rt_render_opts(seed, self.device, sample_offset, sample_count, flags, *(rows or (0, 0, 0)))
         st = abi.rt_stats()
         lib.check(self._lib.rt_render_accum_device(self._h, C.byref(cam), C.byref(opts), C.c_void_p(d_accum_ptr),
                                                    C.byref(st)))
@@ -96,14 +102,17 @@ class Scene:
         return nodes, ids, info
 
 
-def render_multi(data, cam, devices, seed=scenes.RENDER_SEED, sample_offset=0, sample_count=0, want_accum=False):
-    """rt_render_multi: one call, several GPUs (sample-split inside the library)."""
+def render_multi(data, cam, devices, seed=scenes.RENDER_SEED, sample_offset=0, sample_count=0, want_accum=False,
+                 tile_split=False):
+    """rt_render_multi: one call, several GPUs (sample-split inside the library, or interleaved
+    scanlines with tile_split=True: bit-identical to the single-GPU render)."""
     desc, keep = data.to_desc()
     H, W = cam.height, cam.width
     rgb = np.empty((H, W, 3), np.uint8)
     acc = np.empty((H, W, 3), np.float32) if want_accum else None
     devs = (C.c_int32 * len(devices))(*devices)
-    opts = abi.rt_render_opts(seed, devices[0], sample_offset, sample_count, 0)
+    opts = abi.rt_render_opts(seed, devices[0], sample_offset, sample_count,
+                              abi.RT_FLAG_TILE_SPLIT if tile_split else 0)
     st = abi.rt_stats()
     lib.check(lib.load().rt_render_multi(C.byref(desc), C.byref(cam), C.byref(opts), devs, len(devices),
                                          rgb.ctypes.data_as(C.c_void_p),

@@ -506,13 +506,34 @@ static int scene_events(rt_scene *s, size_t n) {
     return RT_OK;
 }
 
+// The scanlines a call renders (rt_render_opts.row_*): image row = begin + k * step, k in [0, count).
+struct RowSet {
+    int begin, count, step;
+};
+static int row_set(const rt_camera *cam, const rt_render_opts *opts, RowSet *rs) {
+    if (opts->row_count == 0) {
+        rs->begin = 0, rs->count = cam->height, rs->step = 1;
+        return RT_OK;
+    }
+    rs->begin = opts->row_begin, rs->count = opts->row_count, rs->step = opts->row_step;
+    if (rs->count < 0 || rs->begin < 0 || rs->step < 1 ||
+        (int64_t)rs->begin + (int64_t)(rs->count - 1) * rs->step >= (int64_t)cam->height)
+        return fail(RT_ERR_INVALID_ARGUMENT, "row set (begin %d, count %d, step %d) outside the %d image rows", rs->begin,
+                    rs->count, rs->step, cam->height);
+    return RT_OK;
+}
+
 #define RT_PASS_PATHS (64u << 20) /* paths per pass: 1 GiB of float4 radiances + 3 GiB of survivor queue; measured
                                      on C2: 16 / 32 / 64 Mi paths per pass = 3377 / 3482 / 3557 Msamples/s (fewer tails) */
 
-// Accumulate samples [sample_offset, +sample_count) of every pixel into d_accum (device, W*H*3).
+// Accumulate samples [sample_offset, +sample_count) of every pixel of the call's row set into
+// d_accum (device, rows*W*3, compact).
 static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts *opts, float *d_accum,
                         rt_stats *stats, uint32_t *launches) {
-    const uint32_t n_pix = (uint32_t)cam->width * (uint32_t)cam->height;
+    RowSet rows;
+    int rc = row_set(cam, opts, &rows);
+    if (rc != RT_OK) return rc;
+    const uint32_t n_pix = (uint32_t)cam->width * (uint32_t)rows.count;
     const int spp = opts->sample_count > 0 ? opts->sample_count : cam->spp;
     if (spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "sample count %d < 1", spp);
     if (opts->sample_offset < 0) return fail(RT_ERR_INVALID_ARGUMENT, "negative sample_offset");
@@ -520,7 +541,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     // the camera may sit outside the radius the BVH was padded for
     const float lens = std::sqrt(cam->defocus_u[0] * cam->defocus_u[0] + cam->defocus_u[1] * cam->defocus_u[1] +
                                  cam->defocus_u[2] * cam->defocus_u[2]);
-    int rc = ensure_origin_radius(s, dist_to_center(s, cam->center) + 2.0 * lens);
+    rc = ensure_origin_radius(s, dist_to_center(s, cam->center) + 2.0 * lens);
     if (rc != RT_OK) return rc;
 
     const uint32_t budget = (uint32_t)std::max(1, env_int("RT_B200_PASS_PATHS", (int)RT_PASS_PATHS));
@@ -543,6 +564,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.sc = s->dev;
     p.cam = make_dev_camera(*cam);
     p.seed = opts->seed;
+    p.row_begin = (uint32_t)rows.begin, p.row_step = (uint32_t)rows.step;
     p.samples = ws.samples;
     p.counter = s->d_counter;
     p.stats = s->d_stats;
@@ -647,7 +669,11 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
     Workspace &ws = g_ws[scene->device];
     std::lock_guard<std::mutex> lock(ws.mu);
     if (stats) memset(stats, 0, sizeof *stats);
-    const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)camera->height;
+    RowSet rows;
+    rc = row_set(camera, opts, &rows);
+    if (rc != RT_OK) return rc;
+    const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)rows.count;
+    if (n_pix == 0) return RT_OK;
     const int spp = opts->sample_count > 0 ? opts->sample_count : camera->spp;
     rc = ws_reserve(ws.accum, ws.accum_cap, (size_t)n_pix * 3);
     if (rc == RT_OK) rc = ws_reserve(ws.rgb, ws.rgb_cap, (size_t)n_pix * 3);
@@ -678,10 +704,14 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
 // ---------------------------------------------------------------------------------------------
 // one call, several GPUs (what a single host process such as the Go program needs)
 // ---------------------------------------------------------------------------------------------
-// Sample-split inside the library: device k renders its share of camera->spp into its
-// own FP32 accumulator on its own host thread; the accumulators are peer-copied to devices[0] and
-// added in device order (deterministic), devices[0] resolves.  Every (pixel, sample) keeps the
-// Philox stream it has in a single-GPU render, so only the FP32 summation order differs.
+// Inside the library, on one host thread per device:
+//  * sample-split (default): device k renders its share of the samples of every pixel into its own
+//    FP32 accumulator; the accumulators are peer-copied to devices[0] and added in device order
+//    (deterministic), devices[0] resolves.  Every (pixel, sample) keeps the Philox stream it has in
+//    a single-GPU render, so only the FP32 summation order differs.
+//  * tile-split (RT_FLAG_TILE_SPLIT): device k renders scanlines k, k+n, k+2n, ... at all samples
+//    and resolves them itself; the host interleaves the rows.  No exchange between devices, and the
+//    image is bit-identical to the single-GPU render.
 extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
                                const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
                                rt_stats *stats) {
@@ -691,6 +721,9 @@ extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camer
     const double t0 = now_ms();
     const int spp = opts->sample_count > 0 ? opts->sample_count : camera->spp;
     if (spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "sample count %d < 1", spp);
+    RowSet rows;
+    rc = row_set(camera, opts, &rows);
+    if (rc != RT_OK) return rc;
     std::vector<int> devs(devices, devices + n_devices);
     {
         std::vector<int> sorted = devs;
@@ -700,8 +733,11 @@ extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camer
         for (int d : sorted)
             if (d < 0 || d >= RT_MAX_DEVICES) return fail(RT_ERR_INVALID_ARGUMENT, "device %d out of range", d);
     }
-    const size_t n_acc = (size_t)camera->width * camera->height * 3;
-    const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)camera->height;
+    const bool tiles = (opts->flags & RT_FLAG_TILE_SPLIT) != 0;
+    const size_t row_bytes = (size_t)camera->width * 3;
+    const size_t n_acc = (size_t)rows.count * row_bytes;
+    const uint32_t n_pix = (uint32_t)camera->width * (uint32_t)rows.count;
+    if (n_pix == 0) return RT_OK;
 
     // workspaces are locked in ascending device order (no lock-order inversion between calls)
     std::vector<int> order = devs;
@@ -713,6 +749,7 @@ extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camer
         rt_scene *scene = nullptr;
         rt_render_opts o;
         rt_stats st;
+        bool idle = false; // more devices than samples / rows
         int rc = RT_OK;
         std::string err;
     };
@@ -723,23 +760,50 @@ extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camer
         Job &j = jobs[k];
         j.o = *opts;
         j.o.device = devs[k];
-        j.o.sample_count = base + (k < rem ? 1 : 0);
-        j.o.sample_offset = opts->sample_offset + k * base + std::min(k, rem);
+        j.o.flags &= ~RT_FLAG_TILE_SPLIT;
+        j.o.row_begin = rows.begin, j.o.row_count = rows.count, j.o.row_step = rows.step;
+        if (tiles) { // rows k, k+n, ... of the caller's row set
+            j.o.row_begin = rows.begin + k * rows.step;
+            j.o.row_step = rows.step * n_devices;
+            j.o.row_count = (rows.count - k + n_devices - 1) / n_devices;
+            j.o.sample_count = spp;
+            j.idle = j.o.row_count <= 0;
+        } else {
+            j.o.sample_count = base + (k < rem ? 1 : 0);
+            j.o.sample_offset = opts->sample_offset + k * base + std::min(k, rem);
+            j.idle = j.o.sample_count == 0;
+        }
         memset(&j.st, 0, sizeof j.st);
         threads.emplace_back([&, k]() {
             Job &jj = jobs[k];
-            if (jj.o.sample_count == 0) return; // more devices than samples
+            if (jj.idle) return;
             jj.rc = rt_scene_create(desc, devs[k], &jj.scene);
             if (jj.rc == RT_OK) {
                 Workspace &ws = g_ws[devs[k]];
-                jj.rc = ws_reserve(ws.accum, ws.accum_cap, n_acc);
+                const size_t my_acc = (size_t)jj.o.row_count * row_bytes;
+                jj.rc = ws_reserve(ws.accum, ws.accum_cap, my_acc);
+                if (jj.rc == RT_OK && tiles) jj.rc = ws_reserve(ws.rgb, ws.rgb_cap, my_acc);
+                if (jj.rc == RT_OK && tiles) jj.rc = ws_reserve(ws.h_rgb, ws.h_rgb_cap, my_acc, true);
+                if (jj.rc == RT_OK && tiles && accum_out) jj.rc = ws_reserve(ws.h_accum, ws.h_accum_cap, my_acc, true);
                 uint32_t launches = 0;
+                cudaStream_t st = jj.scene->stream;
                 if (jj.rc == RT_OK) jj.rc = scene_events(jj.scene, 2);
-                if (jj.rc == RT_OK) jj.rc = cudaEventRecord(jj.scene->events[0], jj.scene->stream) == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+                if (jj.rc == RT_OK) jj.rc = cudaEventRecord(jj.scene->events[0], st) == cudaSuccess ? RT_OK : RT_ERR_CUDA;
                 if (jj.rc == RT_OK) jj.rc = render_accum(jj.scene, camera, &jj.o, ws.accum, &jj.st, &launches);
                 if (jj.rc == RT_OK) {
-                    cudaEventRecord(jj.scene->events[1], jj.scene->stream);
-                    if (cudaStreamSynchronize(jj.scene->stream) != cudaSuccess) jj.rc = fail(RT_ERR_CUDA, "render failed on device %d", devs[k]);
+                    cudaError_t e = cudaSuccess;
+                    if (tiles) {
+                        const uint32_t my_pix = (uint32_t)(my_acc / 3);
+                        resolve_kernel<<<(my_pix + 255) / 256, 256, 0, st>>>(ws.accum, ws.rgb, my_pix, 1.0f / (float)spp);
+                        launches++;
+                        e = cudaGetLastError();
+                    }
+                    if (e == cudaSuccess) e = cudaEventRecord(jj.scene->events[1], st);
+                    if (e == cudaSuccess && tiles) e = cudaMemcpyAsync(ws.h_rgb, ws.rgb, my_acc, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess && tiles && accum_out)
+                        e = cudaMemcpyAsync(ws.h_accum, ws.accum, my_acc * sizeof(float), cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                    if (e != cudaSuccess) jj.rc = fail(RT_ERR_CUDA, "render failed on device %d: %s", devs[k], cudaGetErrorString(e));
                     else cudaEventElapsedTime(&jj.st.ms_render, jj.scene->events[0], jj.scene->events[1]);
                     jj.st.kernel_launches = launches;
                 }
@@ -760,38 +824,49 @@ extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camer
             return fail(code, "%s", msg.c_str());
         }
 
-    // gather on devices[0]: peer copy + add, in device order
-    const int root = devs[0];
-    Workspace &w0 = g_ws[root];
-    cudaError_t e = cudaSetDevice(root);
-    float *tmp = nullptr;
-    if (e == cudaSuccess && n_devices > 1) e = cudaMalloc(&tmp, n_acc * sizeof(float));
-    cudaStream_t st0 = jobs[0].scene->stream;
-    for (int k = 1; k < n_devices && e == cudaSuccess; k++) {
-        if (jobs[k].o.sample_count == 0) continue;
-        e = cudaMemcpyPeerAsync(tmp, root, g_ws[devs[k]].accum, devs[k], n_acc * sizeof(float), st0);
-        if (e == cudaSuccess) {
-            add_kernel<<<(unsigned)((n_acc + 255) / 256), 256, 0, st0>>>(w0.accum, tmp, n_acc);
-            e = cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (tiles) {
+        // row r of the caller's row set was rendered by device r % n as its local row r / n
+        for (int r = 0; r < rows.count; r++) {
+            const Workspace &w = g_ws[devs[r % n_devices]];
+            const size_t local = (size_t)(r / n_devices) * row_bytes;
+            memcpy(rgb_out + (size_t)r * row_bytes, w.h_rgb + local, row_bytes);
+            if (accum_out) memcpy(accum_out + (size_t)r * row_bytes, w.h_accum + local, row_bytes * sizeof(float));
         }
-    }
-    if (e == cudaSuccess) {
-        rc = ws_reserve(w0.rgb, w0.rgb_cap, (size_t)n_pix * 3);
-        if (rc == RT_OK) rc = ws_reserve(w0.h_rgb, w0.h_rgb_cap, (size_t)n_pix * 3, true);
-        if (rc == RT_OK && accum_out) rc = ws_reserve(w0.h_accum, w0.h_accum_cap, n_acc, true);
-        if (rc == RT_OK) {
-            resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st0>>>(w0.accum, w0.rgb, n_pix, 1.0f / (float)spp);
-            e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaMemcpyAsync(w0.h_rgb, w0.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st0);
-            if (e == cudaSuccess && accum_out) e = cudaMemcpyAsync(w0.h_accum, w0.accum, n_acc * sizeof(float), cudaMemcpyDeviceToHost, st0);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+    } else {
+        // gather on devices[0]: peer copy + add, in device order
+        const int root = devs[0];
+        Workspace &w0 = g_ws[root];
+        e = cudaSetDevice(root);
+        float *tmp = nullptr;
+        if (e == cudaSuccess && n_devices > 1) e = cudaMalloc(&tmp, n_acc * sizeof(float));
+        cudaStream_t st0 = jobs[0].scene->stream;
+        for (int k = 1; k < n_devices && e == cudaSuccess; k++) {
+            if (jobs[k].idle) continue;
+            e = cudaMemcpyPeerAsync(tmp, root, g_ws[devs[k]].accum, devs[k], n_acc * sizeof(float), st0);
             if (e == cudaSuccess) {
-                memcpy(rgb_out, w0.h_rgb, (size_t)n_pix * 3);
-                if (accum_out) memcpy(accum_out, w0.h_accum, n_acc * sizeof(float));
+                add_kernel<<<(unsigned)((n_acc + 255) / 256), 256, 0, st0>>>(w0.accum, tmp, n_acc);
+                e = cudaGetLastError();
             }
         }
+        if (e == cudaSuccess) {
+            rc = ws_reserve(w0.rgb, w0.rgb_cap, (size_t)n_pix * 3);
+            if (rc == RT_OK) rc = ws_reserve(w0.h_rgb, w0.h_rgb_cap, (size_t)n_pix * 3, true);
+            if (rc == RT_OK && accum_out) rc = ws_reserve(w0.h_accum, w0.h_accum_cap, n_acc, true);
+            if (rc == RT_OK) {
+                resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st0>>>(w0.accum, w0.rgb, n_pix, 1.0f / (float)spp);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaMemcpyAsync(w0.h_rgb, w0.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st0);
+                if (e == cudaSuccess && accum_out) e = cudaMemcpyAsync(w0.h_accum, w0.accum, n_acc * sizeof(float), cudaMemcpyDeviceToHost, st0);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+                if (e == cudaSuccess) {
+                    memcpy(rgb_out, w0.h_rgb, (size_t)n_pix * 3);
+                    if (accum_out) memcpy(accum_out, w0.h_accum, n_acc * sizeof(float));
+                }
+            }
+        }
+        if (tmp) cudaFree(tmp);
     }
-    if (tmp) cudaFree(tmp);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         for (auto &j : jobs) {

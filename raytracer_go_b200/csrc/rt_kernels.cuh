@@ -87,7 +87,9 @@ struct RenderParams {
     DevScene sc;
     DevCamera cam;
     uint64_t seed;
-    uint32_t pixel_begin;  // first pixel of this pass (row-major index)
+    uint32_t pixel_begin;  // first pixel of this pass (row-major index within the call's row set)
+    uint32_t row_begin;    // row set of the call (rt_render_opts): image row = row_begin + local row * row_step
+    uint32_t row_step;
     uint32_t sample_begin; // global index of the first sample of this pass
     uint32_t spp_pass;     // samples per pixel in this pass
     uint32_t total_paths;  // n_pixels_pass * spp_pass
@@ -108,6 +110,16 @@ struct RenderParams {
     int stage_depth; // segments already traced for the paths a stage kernel processes
     size_t queue_stride; // elements per queue array (host-side bookkeeping)
 };
+
+// Pixel `lp` of the call's row set (compact, row-major) -> its index in the full image: the Philox
+// counter and the camera ray use the full-image position, so a row set reproduces those rows of the
+// full render exactly.  Contiguous rows (row_step 1, every single-GPU render) need no division.
+__device__ __forceinline__ uint32_t image_pixel(const RenderParams &p, uint32_t lp) {
+    const uint32_t w = (uint32_t)p.cam.width;
+    if (p.row_step == 1) return p.row_begin * w + lp;
+    const uint32_t jl = lp / w;
+    return (p.row_begin + jl * p.row_step) * w + (lp - jl * w);
+}
 
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
 #define RT_MAX_STAGES 8 /* coherent stage kernels before the megakernel (staged mode) */
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                     const float4 qo = p.queue_o[e], qd = p.queue_d[e], qt = p.queue_t[e];
                     idx = __float_as_uint(qo.w);
                     const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-                    rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + k);
+                    rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
                     rng.block = __float_as_uint(qd.w);
                     o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z);
                     thr = v3(qt.x, qt.y, qt.z), rad = v3(0, 0, 0), depth = p.stage_depth;
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                 } else {
                     idx = warp_next + rank;
                     const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-                    const uint32_t pixel = p.pixel_begin + pp;
+                    const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
                     const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
                     rng.init(p.seed, pixel, p.sample_begin + k);
                     generate_ray(p.cam, rng, i, j, o, d);
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
             V3 rad = v3(0, 0, 0);
             if (FIRST) {
                 const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-                const uint32_t pixel = p.pixel_begin + pp;
+                const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
                 const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
                 rng.init(p.seed, pixel, p.sample_begin + k);
                 generate_ray(p.cam, rng, i, j, o, d);
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 const float4 qo = p.in_o[item], qd = p.in_d[item], qt = p.in_t[item];
                 idx = __float_as_uint(qo.w);
                 const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
-                rng.init(p.seed, p.pixel_begin + pp, p.sample_begin + k);
+                rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
                 rng.block = __float_as_uint(qd.w);
                 o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z), thr = v3(qt.x, qt.y, qt.z);
                 if (qt.w != 0.0f) { // radiance parked by an earlier stage

@@ -42,6 +42,11 @@ import (
 type B200Options struct {
 	Seed   uint64
 	Device int
+	// Devices, when it lists more than one CUDA ordinal, renders on all of them from this one
+	// call (rt_render_multi).  TileSplit gives every device interleaved scanlines instead of a
+	// share of the samples: the image is then bit-identical to the single-GPU one.
+	Devices   []int
+	TileSplit bool
 }
 
 type b200Flat struct {
@@ -280,12 +285,6 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 		sphere_ids: (*C.uint32_t)(psi), quad_ids: (*C.uint32_t)(pqi),
 		perlins: (*C.rt_perlin)(ppl), n_perlins: C.uint32_t(len(f.perlins)),
 	}
-	var scene *C.rt_scene
-	if rc := C.rt_scene_create(&desc, C.int(o.Device), &scene); rc != C.RT_OK {
-		return lastB200Error(rc)
-	}
-	defer C.rt_scene_destroy(scene)
-
 	v3 := func(v Vec3) [3]C.float { return [3]C.float{C.float(v.X), C.float(v.Y), C.float(v.Z)} }
 	w, h := int(c.imageWidth), int(c.imageHeight) // camera.go:181-182
 	cam := C.rt_camera{
@@ -297,8 +296,27 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 	}
 	ropts := C.rt_render_opts{seed: C.uint64_t(o.Seed), device: C.int32_t(o.Device)}
 	rgb := make([]byte, 3*w*h)
-	if rc := C.rt_render(scene, &cam, &ropts, (*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil); rc != C.RT_OK {
-		return lastB200Error(rc)
+	if len(o.Devices) > 1 { // the whole box from one call
+		devs := make([]C.int32_t, len(o.Devices))
+		for i, d := range o.Devices {
+			devs[i] = C.int32_t(d)
+		}
+		if o.TileSplit {
+			ropts.flags = C.RT_FLAG_TILE_SPLIT
+		}
+		if rc := C.rt_render_multi(&desc, &cam, &ropts, &devs[0], C.int32_t(len(devs)),
+			(*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil); rc != C.RT_OK {
+			return lastB200Error(rc)
+		}
+	} else {
+		var scene *C.rt_scene
+		if rc := C.rt_scene_create(&desc, C.int(o.Device), &scene); rc != C.RT_OK {
+			return lastB200Error(rc)
+		}
+		defer C.rt_scene_destroy(scene)
+		if rc := C.rt_render(scene, &cam, &ropts, (*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil); rc != C.RT_OK {
+			return lastB200Error(rc)
+		}
 	}
 
 	// from here on: the reference's own output path (camera.go:183-191, 225, 237-252)

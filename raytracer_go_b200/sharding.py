@@ -9,8 +9,9 @@ render's sample set.
   sample-split  rank r renders global samples [offset, offset+count) of every pixel into a private
                 FP32 W*H*3 accumulator; ONE reduce(sum) to rank 0, which resolves with the total
                 spp.  This is the path's only exchange step.
-  tile-split    rank r renders a contiguous band of scanlines at full spp; no reduction, the bands
-                are gathered (concatenated) on rank 0.
+  tile-split    rank r renders scanlines r, r+N, r+2N, ... at full spp (interleaved: sky rows are
+                cheap, ground rows are not, contiguous bands would not balance); no reduction, the
+                rows are gathered on rank 0 and interleaved.  Bit-identical to the single-GPU render.
 """
 
 
@@ -33,6 +34,35 @@ def tile_split(rank, world, height):
     rows = base + (1 if rank < rem else 0)
     begin = rank * base + min(rank, rem)
     return begin, begin + rows
+
+
+def row_split(rank, world, height):
+    """Interleaved scanlines: (row_begin, row_count, row_step) for rt_render_opts."""
+    return rank, max(0, (height - rank + world - 1) // world), world
+
+
+def gather_rows(local, height, dst=0):
+    """The tile-split exchange: every rank holds its row_split() rows as a (row_count, W, C) tensor;
+    returns the (height, W, C) image on `dst` (None elsewhere).  One gather, no arithmetic."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank()
+    most = (height + world - 1) // world  # ranks may differ by one row: pad to the largest share
+    padded = local
+    if local.shape[0] < most:
+        padded = torch.cat([local, local.new_zeros((most - local.shape[0],) + tuple(local.shape[1:]))])
+    parts = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded.contiguous(), parts, dst=dst)
+    if rank != dst:
+        return None
+    out = local.new_empty((height,) + tuple(local.shape[1:]))
+    for r in range(world):
+        _, count, step = row_split(r, world, height)
+        out[r::step] = parts[r][:count]
+    return out
 
 
 def reduce_accumulators(accum, dst=0):

@@ -374,6 +374,42 @@ def test_render_multi_two_devices(gpu, random_scene):
     assert np.allclose(acc3, acc, rtol=2e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("rows", [(0, 112, 1), (5, 40, 1), (1, 56, 2), (2, 37, 3), (111, 1, 1), (3, 14, 8)])
+def test_row_set_is_those_rows_of_the_full_render(gpu, random_scene, rows):
+    """rt_render_opts.row_*: a row set (contiguous band or interleaved scanlines, SURVEY §8e tile-split)
+    is bit-identical to the same rows of the full render, accumulators included."""
+    cam = _cam(200, 5)
+    assert cam.height == 112
+    b, n, step = rows
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+        part, pacc, pst = sc.render(cam, SEED, want_accum=True, rows=(b, n, step))
+    assert part.shape == (n, cam.width, 3)
+    assert np.array_equal(part, rgb[b:b + n * step:step])
+    assert np.array_equal(pacc.view(np.uint32), acc[b:b + n * step:step].view(np.uint32))
+    assert pst.samples == n * cam.width * 5
+
+
+def test_row_set_errors(gpu, random_scene):
+    cam = _cam(64, 2)
+    with api.Scene(random_scene) as sc:
+        for bad in [(-1, 4, 1), (0, cam.height + 1, 1), (0, 4, 0), (cam.height - 1, 2, 1), (0, cam.height, 2)]:
+            with pytest.raises(RuntimeError, match="row set"):
+                sc.render(cam, SEED, rows=bad)
+
+
+def test_render_multi_tile_split_is_bitwise_the_single_gpu_image(gpu, random_scene):
+    """RT_FLAG_TILE_SPLIT: interleaved scanlines per device, no exchange; on any number of devices the
+    image and the accumulators are bit-identical to rt_render."""
+    cam = _cam(320, 7)
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    devices = list(range(min(gpu, 8)))
+    rgb2, acc2, st2 = api.render_multi(random_scene, cam, devices, SEED, want_accum=True, tile_split=True)
+    assert np.array_equal(rgb2, rgb) and np.array_equal(acc2.view(np.uint32), acc.view(np.uint32))
+    assert st2.samples == st.samples and st2.rays == st.rays and st2.hits == st.hits
+
+
 def test_binary_ppm_equals_text_ppm(gpu):
     """RenderP6 (binary PPM, the reference's TODO at camera.go:196) carries the pixels of Render's P3."""
     import io

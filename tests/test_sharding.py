@@ -33,6 +33,17 @@ def test_tile_split_partition():
             assert rows == list(range(h))
 
 
+def test_row_split_partition():
+    for world in (1, 2, 3, 4, 8, 7):
+        for h in (1, 5, 225, 675, 2160):
+            rows = []
+            for r in range(world):
+                b, n, step = sharding.row_split(r, world, h)
+                assert step == world and (n == 0 or b + (n - 1) * step < h)
+                rows += [b + k * step for k in range(n)]
+            assert sorted(rows) == list(range(h))
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -53,8 +64,15 @@ def _worker(rank, world, port, q):
     bands = [torch.empty((sharding.tile_split(r, world, cam.height)[1] - sharding.tile_split(r, world, cam.height)[0],
                           cam.width, 3), dtype=torch.uint8) for r in range(world)] if rank == 0 else None
     dist.gather(band, bands, dst=0)
+    # interleaved rows (what bench.py --split tile and rt_render_multi's tile mode do); 45 rows on 2 ranks
+    # is a ragged split (23 + 22), which exercises gather_rows' padding
+    rb, rn, rs = sharding.row_split(rank, world, cam.height)
+    whole, _, _ = orc.render(scene, cam, 9, order=orc.ORDER_ITERATIVE, threads=2)  # the oracle has no strided row set
+    mine = torch.from_numpy(whole[rb::rs].copy())
+    assert mine.shape[0] == rn
+    inter = sharding.gather_rows(mine, cam.height, dst=0)
     if rank == 0:
-        q.put((t.numpy(), torch.cat(bands).numpy(), total))
+        q.put((t.numpy(), torch.cat(bands).numpy(), total, inter.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,7 +87,7 @@ def test_two_rank_gloo_sample_and_tile_split(orc):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    acc, tiled, total = q.get(timeout=180)
+    acc, tiled, total, inter = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -80,3 +98,4 @@ def test_two_rank_gloo_sample_and_tile_split(orc):
     np.testing.assert_allclose(acc, full, rtol=2e-6, atol=1e-6)
     assert (np.abs(orc.resolve(acc, total).astype(int) - rgb.astype(int)) <= 1).all()
     assert np.array_equal(tiled, rgb)  # tile-split is bitwise the single-process image
+    assert np.array_equal(inter, rgb)
