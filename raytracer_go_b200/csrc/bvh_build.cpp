@@ -296,6 +296,29 @@ void compute_scene_center(const ScenePrims &prims, double m[3], double *extent90
     *extent90 = v[k90];
 }
 
+// (min, max) boxes -> the (centre, half-extent) form the traversal kernels read.  The centre is rounded
+// to float; the half-extent is taken from that rounded centre, rounded up, and widened by a few ulp of
+// the magnitudes involved for the one extra rounding the centre form has in the slab test
+// (m = (c - o) * inv is rounded before -+ h*|inv| is added).  Culling only has to be conservative.
+static void make_device_nodes(FlatBvh *bvh) {
+    const double U = 5.960464477539063e-08; // 2^-24
+    bvh->dev_nodes.resize(bvh->nodes.size());
+    for (size_t i = 0; i + 1 < bvh->nodes.size(); i += 2) {
+        const F4 &lo = bvh->nodes[i], &hi = bvh->nodes[i + 1];
+        const float l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+        float c[3], e[3];
+        for (int k = 0; k < 3; k++) {
+            c[k] = (float)(0.5 * ((double)l[k] + (double)h[k]));
+            double half = std::max((double)h[k] - (double)c[k], (double)c[k] - (double)l[k]);
+            half += 4.0 * U * (std::fabs((double)c[k]) + half);
+            e[k] = std::nextafter((float)half, POS_INF);
+            if (!((double)c[k] - (double)e[k] <= (double)l[k] && (double)c[k] + (double)e[k] >= (double)h[k])) e[k] = POS_INF; // overflow
+        }
+        F4 a = {c[0], c[1], c[2], lo.w}, b = {e[0], e[1], e[2], 0.0f};
+        bvh->dev_nodes[i] = a, bvh->dev_nodes[i + 1] = b;
+    }
+}
+
 void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out) {
     *out = FlatBvh();
     const size_t n = prims.size();
@@ -323,6 +346,7 @@ void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, 
     out->sph.reserve(prims.spheres.size()), out->meta.reserve(prims.spheres.size());
     Box root_box;
     out->root_ref = b.build(0, n, 0, &root_box);
+    make_device_nodes(out);
 }
 
 // Recompute every box for a larger origin_radius, topology unchanged.  Nodes are in pre-order
@@ -361,6 +385,7 @@ void refit_flat_bvh(const ScenePrims &prims, float origin_radius, FlatBvh *bvh) 
         hi.x = bx.hi[0], hi.y = bx.hi[1], hi.z = bx.hi[2];
     }
     bvh->pad_min = pmin, bvh->pad_max = pmax;
+    make_device_nodes(bvh);
 }
 
 void pack_materials(const rt_scene_desc *d, std::vector<F4> *out) {

@@ -18,7 +18,9 @@ struct ScenePrims {
 };
 
 struct FlatBvh {
-    std::vector<F4> nodes;          // 2 x F4 per node, siblings adjacent, depth-first order
+    std::vector<F4> nodes;          // 2 x F4 per node (min.xyz, ref)(max.xyz, 0), siblings adjacent, depth-first order
+    std::vector<F4> dev_nodes;      // the same nodes as the kernels read them: (centre.xyz, ref)(half-extent.xyz, 0),
+                                    // [c - h, c + h] encloses [min, max] (box_test in rt_trace.h)
     std::vector<F4> sph;            // per sphere slot: centre, radius
     std::vector<I2> meta;           // per sphere slot: object ID, material index
     std::vector<uint32_t> sph_prim; // per sphere slot: index into ScenePrims.spheres

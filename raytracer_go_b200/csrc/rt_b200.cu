@@ -249,8 +249,8 @@ static void free_scene(rt_scene *s) {
 }
 
 static int upload_nodes(rt_scene *s) {
-    if (!s->bvh.nodes.empty())
-        CU(cudaMemcpyAsync(s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(F4), cudaMemcpyHostToDevice, s->stream));
+    if (!s->bvh.dev_nodes.empty())
+        CU(cudaMemcpyAsync(s->d_nodes, s->bvh.dev_nodes.data(), s->bvh.dev_nodes.size() * sizeof(F4), cudaMemcpyHostToDevice, s->stream));
     return RT_OK;
 }
 
@@ -573,10 +573,14 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.queue_o = ws.queue, p.queue_stride = need; // launch_split fills the per-stage pointers
     p.queue_d = p.queue_t = nullptr, p.queue_count = s->d_queue_count;
     p.in_o = p.in_d = p.in_t = nullptr, p.in_count = nullptr, p.stage_depth = 0;
+    const bool balance = env_int("RT_B200_PASS_BALANCE", 1) != 0;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
-        for (uint32_t k0 = 0; k0 < (uint32_t)spp; k0 += spp_pass_max) {
-            const uint32_t sp = std::min(spp_pass_max, (uint32_t)spp - k0);
+        // equal passes (500 spp at 82 per pass = 7 passes of 71-72, not 6 x 82 + 8: a short pass is mostly tail)
+        const uint32_t n_passes = ((uint32_t)spp + spp_pass_max - 1) / spp_pass_max;
+        for (uint32_t k0 = 0, pass = 0, sp = 0; k0 < (uint32_t)spp; k0 += sp, pass++) {
+            sp = balance ? ((uint32_t)spp - k0 + (n_passes - pass) - 1) / (n_passes - pass)
+                         : std::min(spp_pass_max, (uint32_t)spp - k0);
             p.pixel_begin = pb;
             p.sample_begin = (uint32_t)opts->sample_offset + k0;
             p.spp_pass = sp;

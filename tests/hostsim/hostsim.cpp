@@ -83,7 +83,7 @@ int hs_trace(const rt_scene_desc *d, int max_leaf, float origin_radius, const fl
     for (int64_t i = 0; i < n; i++) {
         LocalStack<64> stack;
         HitRec h;
-        trace_closest<LocalStack<64>, true, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
+        trace_closest<LocalStack<64>, true, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
                                                   v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
                                                   v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmin, tmax, stack, h, &wc,
                                                   s.bvh.quad.data());
@@ -113,7 +113,7 @@ int hs_render(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32
             for (int depth = 0; depth < c.max_depth;) {
                 LocalStack<64> stack;
                 HitRec h;
-                trace_closest<LocalStack<64>, false, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
+                trace_closest<LocalStack<64>, false, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
                                                            s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, nullptr,
                                                            s.bvh.quad.data());
                 if (h.slot == RT_REF_NONE) {
@@ -173,7 +173,7 @@ extern "C" int64_t hs_segment_stats(const rt_scene_desc *d, const rt_camera *cam
                 LocalStack<64> stack;
                 HitRec h;
                 WorkCounters wc{0, 0};
-                trace_closest<LocalStack<64>, true>(s.bvh.nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
+                trace_closest<LocalStack<64>, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
                                                     s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, &wc);
                 if (n < max_seg) iters[n] = (int32_t)(wc.box_tests / 2), sph_tests[n] = (int32_t)wc.sphere_tests, depths[n] = depth, n++;
                 if (h.slot == RT_REF_NONE) break;
@@ -196,7 +196,7 @@ extern "C" int64_t hs_traversal_events(const rt_scene_desc *d, const rt_camera *
     load(d, max_leaf, 0, &s);
     DevCamera c = make_dev_camera(*cam);
     int64_t n = 0, rays = 0;
-    const F4 *nodes = s.bvh.nodes.data();
+    const F4 *nodes = s.bvh.dev_nodes.data();
     for (int64_t pp = 0; pp < n_pixels; pp++) {
         int64_t pix = pixel_begin + pp;
         for (int k = 0; k < spp; k++) {
@@ -208,6 +208,7 @@ extern "C" int64_t hs_traversal_events(const rt_scene_desc *d, const rt_camera *
                 // same loop as trace_closest, with event logging
                 const V3 inv = v3(cull_rcp(dir.x), cull_rcp(dir.y), cull_rcp(dir.z));
                 const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+                const V3 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
                 const float a = lensq(dir);
                 float tbest = INFINITY;
                 uint32_t best = RT_REF_NONE, ref = s.bvh.root_ref;
@@ -219,7 +220,7 @@ extern "C" int64_t hs_traversal_events(const rt_scene_desc *d, const rt_camera *
                     while (!(ref & RT_LEAF)) {
                         const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1], r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
                         float tl, tr;
-                        const bool hl = box_test(l0, l1, inv, noi, 0.001f, tbest, tl), hr = box_test(r0, r1, inv, noi, 0.001f, tbest, tr);
+                        const bool hl = box_test(l0, l1, inv, noi, ainv, 0.001f, tbest, tl), hr = box_test(r0, r1, inv, noi, ainv, 0.001f, tbest, tr);
                         const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
                         if (hl && hr) {
                             const bool lf = tl <= tr;
@@ -267,7 +268,7 @@ extern "C" int64_t hs_traversal_events_rays(const rt_scene_desc *d, const rt_cam
     load(d, max_leaf, 0, &s);
     DevCamera c = make_dev_camera(*cam);
     int64_t n = 0, rays = 0;
-    const F4 *nodes = s.bvh.nodes.data();
+    const F4 *nodes = s.bvh.dev_nodes.data();
     for (int64_t pp = 0; pp < n_pixels; pp++) {
         int64_t pix = pixel_begin + pp;
         for (int k = 0; k < spp; k++) {
@@ -281,6 +282,7 @@ extern "C" int64_t hs_traversal_events_rays(const rt_scene_desc *d, const rt_cam
                 ro[0] = o.x, ro[1] = o.y, ro[2] = o.z, ro[3] = dir.x, ro[4] = dir.y, ro[5] = dir.z, ro[6] = (float)depth;
                 const V3 inv = v3(cull_rcp(dir.x), cull_rcp(dir.y), cull_rcp(dir.z));
                 const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+                const V3 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
                 const float a = lensq(dir);
                 float tbest = INFINITY;
                 uint32_t best = RT_REF_NONE, ref = s.bvh.root_ref;
@@ -291,7 +293,7 @@ extern "C" int64_t hs_traversal_events_rays(const rt_scene_desc *d, const rt_cam
                     while (!(ref & RT_LEAF)) {
                         const F4 l0 = nodes[2 * ref], l1 = nodes[2 * ref + 1], r0 = nodes[2 * ref + 2], r1 = nodes[2 * ref + 3];
                         float tl, tr;
-                        const bool hl = box_test(l0, l1, inv, noi, 0.001f, tbest, tl), hr = box_test(r0, r1, inv, noi, 0.001f, tbest, tr);
+                        const bool hl = box_test(l0, l1, inv, noi, ainv, 0.001f, tbest, tl), hr = box_test(r0, r1, inv, noi, ainv, 0.001f, tbest, tr);
                         const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
                         if (hl && hr) {
                             const bool lf = tl <= tr;
