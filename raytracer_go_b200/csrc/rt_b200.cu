@@ -573,10 +573,11 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.queue_o = ws.queue, p.queue_stride = need; // launch_split fills the per-stage pointers
     p.queue_d = p.queue_t = nullptr, p.queue_count = s->d_queue_count;
     p.in_o = p.in_d = p.in_t = nullptr, p.in_count = nullptr, p.stage_depth = 0;
-    const bool balance = env_int("RT_B200_PASS_BALANCE", 1) != 0;
+    const bool balance = env_int("RT_B200_PASS_BALANCE", 0) != 0;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
-        // equal passes (500 spp at 82 per pass = 7 passes of 71-72, not 6 x 82 + 8: a short pass is mostly tail)
+        // RT_B200_PASS_BALANCE=1 makes the passes equal (500 spp at 82 per pass = 7 passes of 71-72 instead of
+        // 6 x 82 + 8); measured 0.3 % slower than the greedy split (profiles/r01y), so it is off by default
         const uint32_t n_passes = ((uint32_t)spp + spp_pass_max - 1) / spp_pass_max;
         for (uint32_t k0 = 0, pass = 0, sp = 0; k0 < (uint32_t)spp; k0 += sp, pass++) {
             sp = balance ? ((uint32_t)spp - k0 + (n_passes - pass) - 1) / (n_passes - pass)

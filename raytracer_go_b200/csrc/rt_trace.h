@@ -68,17 +68,29 @@ struct LocalStack {
 struct StridedStack {
     uint32_t *base; // already offset by the thread index
     int stride;
+#if defined(__CUDA_ARCH__)
+    // 32-bit shared-window addresses: push / pop are one STS / LDS plus one add (a generic pointer
+    // makes ptxas carry the generic and the shared address side by side).  The asm statements are
+    // volatile, so they keep their order; nothing else touches the stack memory.
+    uint32_t base_s, top_s;
+    __device__ __forceinline__ void reset() { base_s = top_s = (uint32_t)__cvta_generic_to_shared(base); }
+    __device__ __forceinline__ void push(uint32_t r) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(top_s), "r"(r));
+        top_s += 4u * (uint32_t)stride;
+    }
+    __device__ __forceinline__ uint32_t pop() {
+        if (top_s == base_s) return RT_REF_NONE;
+        top_s -= 4u * (uint32_t)stride;
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(top_s));
+        return r;
+    }
+#else
     int sp;
-    RT_HD void reset() { sp = 0; }
-    RT_HD void push(uint32_t r) {
-        base[sp * stride] = r;
-        sp++;
-    }
-    RT_HD uint32_t pop() {
-        if (sp == 0) return RT_REF_NONE;
-        sp--;
-        return base[sp * stride];
-    }
+    void reset() { sp = 0; }
+    void push(uint32_t r) { base[sp++ * stride] = r; }
+    uint32_t pop() { return sp == 0 ? RT_REF_NONE : base[--sp * stride]; }
+#endif
 };
 
 RT_HD float rt_fmin(float a, float b) { return fminf(a, b); } // NaN-ignoring: a NaN slab never culls
