@@ -61,6 +61,11 @@ struct LocalStack {
     RT_HD void reset() { sp = 0; }
     RT_HD void push(uint32_t r) { e[sp++] = r; }
     RT_HD uint32_t pop() { return sp > 0 ? e[--sp] : RT_REF_NONE; }
+    RT_HD void push_if(bool c, uint32_t r) {
+        if (c) push(r);
+    }
+    // `keep` when have_next, else the popped entry (RT_REF_NONE when the stack is empty)
+    RT_HD uint32_t next_or_pop(bool have_next, uint32_t keep) { return have_next ? keep : pop(); }
 };
 
 // Per-thread traversal stack in shared memory: entry d of thread t lives at base[d*stride + t],
@@ -85,11 +90,29 @@ struct StridedStack {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(top_s));
         return r;
     }
+    // Predicated forms for the inner traversal step: the lanes of an incoherent warp disagree on
+    // "both children hit / one / none" almost every step, so branches there only add BSSY / BRA /
+    // BSYNC around code that is executed anyway (control flow was 15 % of the issued instructions).
+    __device__ __forceinline__ void push_if(bool c, uint32_t r) {
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(top_s), "r"(r), "r"((uint32_t)c));
+        top_s += c ? 4u * (uint32_t)stride : 0u;
+    }
+    __device__ __forceinline__ uint32_t next_or_pop(bool have_next, uint32_t keep) {
+        const bool do_pop = !have_next && top_s != base_s;
+        top_s -= do_pop ? 4u * (uint32_t)stride : 0u;
+        uint32_t r = have_next ? keep : RT_REF_NONE;
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u32 %0, [%1]; }" : "+r"(r) : "r"(top_s), "r"((uint32_t)do_pop));
+        return r;
+    }
 #else
     int sp;
     void reset() { sp = 0; }
     void push(uint32_t r) { base[sp++ * stride] = r; }
     uint32_t pop() { return sp == 0 ? RT_REF_NONE : base[--sp * stride]; }
+    void push_if(bool c, uint32_t r) {
+        if (c) push(r);
+    }
+    uint32_t next_or_pop(bool have_next, uint32_t keep) { return have_next ? keep : pop(); }
 #endif
 };
 
@@ -187,7 +210,11 @@ RT_HD int32_t slot_object_id(uint32_t slot, const I2 *__restrict__ meta, const F
     return meta[slot].x;
 }
 
-template <class Stack, bool COUNT, bool QUADS = false>
+// PRED: the inner step (both children hit / one / none) as straight-line predicated code instead
+// of branches.  Pays for incoherent warps, whose lanes disagree nearly every step (secondary
+// megakernel, shared-memory stack: +1.4 % on C2); costs for coherent warps and for the
+// local-memory stack (C4: -3.5 %), which keep the branches.
+template <class Stack, bool COUNT, bool QUADS = false, bool PRED = false>
 RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sph,
                          const I2 *__restrict__ meta, uint32_t root_ref, V3 o, V3 d, float tmin,
                          float tmax, Stack &stack, HitRec &hit, WorkCounters *wc,
@@ -213,7 +240,12 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
             const bool hr = box_test(r0, r1, inv, noi, ainv, tmin, tbest, tr);
             if (COUNT) wc->box_tests += 2;
             const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
-            if (hl && hr) {
+            // nearer child first, the other one (if hit) on the stack; nothing hit: pop
+            if (PRED) {
+                const bool take_l = hl && (tl <= tr || !hr);
+                stack.push_if(hl && hr, take_l ? rref : lref);
+                ref = stack.next_or_pop(hl || hr, take_l ? lref : rref);
+            } else if (hl && hr) {
                 const bool left_first = tl <= tr;
                 stack.push(left_first ? rref : lref);
                 ref = left_first ? lref : rref;
