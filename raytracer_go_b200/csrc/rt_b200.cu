@@ -523,6 +523,16 @@ static int row_set(const rt_camera *cam, const rt_render_opts *opts, RowSet *rs)
     return RT_OK;
 }
 
+// Philox round keys of a seed -> the device's constant array (rt_rng.h).  Every launch that draws
+// random numbers is preceded by this on its own stream; callers hold the device's workspace lock, so
+// at most one seed is in use per device at a time.
+static int upload_round_keys(uint64_t seed, cudaStream_t stream) {
+    uint32_t rk[2 * RT_PHILOX_ROUNDS];
+    philox_round_keys(seed, rk);
+    CU(cudaMemcpyToSymbolAsync(c_philox_rk, rk, sizeof rk, 0, cudaMemcpyHostToDevice, stream));
+    return RT_OK;
+}
+
 #define RT_PASS_PATHS (64u << 20) /* paths per pass: 1 GiB of float4 radiances + 3 GiB of survivor queue; measured
                                      on C2: 16 / 32 / 64 Mi paths per pass = 3377 / 3482 / 3557 Msamples/s (fewer tails) */
 
@@ -559,6 +569,8 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
         if (stats) stats->samples = (uint64_t)n_pix * (uint64_t)spp;
         return RT_OK;
     }
+    rc = upload_round_keys(opts->seed, s->stream);
+    if (rc != RT_OK) return rc;
     size_t n_ev = 2; // events 0 and 1 bracket the whole call
     RenderParams p;
     p.sc = s->dev;
@@ -952,6 +964,10 @@ extern "C" int rt_primary_rays(const rt_camera *camera, const rt_render_opts *op
     if (rc != RT_OK) return rc;
     const int64_t n = n_pixels * spp;
     if (n == 0) return RT_OK;
+    if (opts->device >= RT_MAX_DEVICES) return fail(RT_ERR_INVALID_ARGUMENT, "device ordinal too large");
+    std::lock_guard<std::mutex> lock(g_ws[opts->device].mu); // the round keys are per device
+    rc = upload_round_keys(opts->seed, 0);
+    if (rc != RT_OK) return rc;
     float *d_o = nullptr, *d_d = nullptr;
     cudaError_t e = cudaMalloc(&d_o, (size_t)n * 12);
     if (e == cudaSuccess) e = cudaMalloc(&d_d, (size_t)n * 12);

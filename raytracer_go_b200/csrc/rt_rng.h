@@ -23,29 +23,55 @@ struct RngBlock {
     float u0, u1, u2, u3;
 };
 
+// The ten round keys (k0 + r*W0, k1 + r*W1) depend on the seed only.  On the device they live in
+// constant memory (philox_round_keys() fills the array, the host uploads it before a launch), so
+// the xor of a round takes its key as a constant-bank operand: no key registers, no 18 key adds
+// per block.  The host build (tests/hostsim) keeps them in a thread-local array.
+#define RT_PHILOX_ROUNDS 10
+RT_HD void philox_round_keys(uint64_t seed, uint32_t *rk) {
+    uint32_t q0 = (uint32_t)seed, q1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < RT_PHILOX_ROUNDS; r++) {
+        rk[2 * r] = q0, rk[2 * r + 1] = q1;
+        q0 += 0x9E3779B9u;
+        q1 += 0xBB67AE85u;
+    }
+}
+#if defined(__CUDACC__)
+static __constant__ uint32_t c_philox_rk[2 * RT_PHILOX_ROUNDS];
+#endif
+#if !defined(__CUDA_ARCH__)
+static thread_local uint32_t h_philox_rk[2 * RT_PHILOX_ROUNDS];
+#endif
+
 struct PathRng {
     uint32_t pixel, sample, block;
-    uint32_t k0, k1;
 
+    // `seed` must be the seed whose round keys are loaded (device: the launch's constant array)
     RT_HD void init(uint64_t seed, uint32_t pixel_, uint32_t sample_) {
         pixel = pixel_, sample = sample_, block = 0;
-        k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#if !defined(__CUDA_ARCH__)
+        philox_round_keys(seed, h_philox_rk);
+#else
+        (void)seed;
+#endif
     }
     RT_HD static float to_f32(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
     // next block of the stream as four uniforms on [0,1) (rand.Float32(), camera.go:290-291)
     RT_HD RngBlock next() {
         uint32_t c0 = pixel, c1 = sample, c2 = block, c3 = 0;
-        uint32_t q0 = k0, q1 = k1;
+#if defined(__CUDA_ARCH__)
+        const uint32_t *rk = c_philox_rk;
+#else
+        const uint32_t *rk = h_philox_rk;
+#endif
 #pragma unroll
-        for (int r = 0; r < 10; r++) {
+        for (int r = 0; r < RT_PHILOX_ROUNDS; r++) {
             // one 32x32->64 multiply per half (IMAD.WIDE.U32), high word xor-ed, low word passed on
             const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
             const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ q0;
-            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ q1;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
             c0 = n0, c1 = (uint32_t)p1, c2 = n2, c3 = (uint32_t)p0;
-            q0 += 0x9E3779B9u;
-            q1 += 0xBB67AE85u;
         }
         block++;
         RngBlock b;
