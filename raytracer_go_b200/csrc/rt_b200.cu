@@ -597,6 +597,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
             p.pixel_begin = pb;
             p.sample_begin = (uint32_t)opts->sample_offset + k0;
             p.spp_pass = sp;
+            p.div_spp = fast_div_magic(sp), p.div_width = fast_div_magic((uint32_t)cam->width);
             p.total_paths = np * sp;
             CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), s->stream));
             rc = scene_events(s, n_ev + 2);

@@ -96,6 +96,7 @@ struct RenderParams {
     float4 *samples;       // [total_paths] radiance of path (pixel - pixel_begin) * spp_pass + k
     unsigned int *counter; // next unclaimed path index
     unsigned long long *stats; // rays, hits, box tests, sphere tests
+    uint64_t div_spp, div_width; // fast_div multipliers of spp_pass and cam.width (host: fast_div_magic)
     uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
     uint32_t chunk;        // work items a warp claims per atomic (RT_CHUNK by default)
     // two-stage mode (primary_stage_kernel + render_kernel<SPLIT>): paths that survive their first
@@ -110,6 +111,15 @@ struct RenderParams {
     int stage_depth; // segments already traced for the paths a stage kernel processes
     size_t queue_stride; // elements per queue array (host-side bookkeeping)
 };
+
+// n / d for 32-bit n by one 64x32-bit multiply-high (Lemire & Kaser 2019: M = floor((2^64-1)/d) + 1,
+// exact for every 32-bit n and d >= 2; d == 1 is encoded as M == 0).  The path index -> (pixel,
+// sample) and pixel -> (row, column) divisions run once per path; a hardware-less 32-bit divide is
+// ~16 instructions, this is ~4.
+static inline uint64_t fast_div_magic(uint32_t d) { return d <= 1 ? 0ull : 0xFFFFFFFFFFFFFFFFull / d + 1ull; }
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic) {
+    return magic == 0 ? n : (uint32_t)__umul64hi(magic, (unsigned long long)n);
+}
 
 // Pixel `lp` of the call's row set (compact, row-major) -> its index in the full image: the Philox
 // counter and the camera ray use the full-image position, so a row set reproduces those rows of the
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                     const uint32_t e = warp_next + rank;
                     const float4 qo = p.queue_o[e], qd = p.queue_d[e], qt = p.queue_t[e];
                     idx = __float_as_uint(qo.w);
-                    const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                    const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                     rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
                     rng.block = __float_as_uint(qd.w);
                     o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z);
@@ -192,9 +202,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                     }
                 } else {
                     idx = warp_next + rank;
-                    const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                    const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                     const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
-                    const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+                    const int j = (int)fast_div(pixel, p.div_width), i = (int)(pixel - (uint32_t)j * p.cam.width);
                     rng.init(p.seed, pixel, p.sample_begin + k);
                     generate_ray(p.cam, rng, i, j, o, d);
                     thr = v3(1, 1, 1), rad = v3(0, 0, 0), depth = 0;
@@ -296,15 +306,15 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
             PathRng rng;
             V3 rad = v3(0, 0, 0);
             if (FIRST) {
-                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                 const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
-                const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+                const int j = (int)fast_div(pixel, p.div_width), i = (int)(pixel - (uint32_t)j * p.cam.width);
                 rng.init(p.seed, pixel, p.sample_begin + k);
                 generate_ray(p.cam, rng, i, j, o, d);
             } else {
                 const float4 qo = p.in_o[item], qd = p.in_d[item], qt = p.in_t[item];
                 idx = __float_as_uint(qo.w);
-                const uint32_t pp = idx / p.spp_pass, k = idx - pp * p.spp_pass;
+                const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                 rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
                 rng.block = __float_as_uint(qd.w);
                 o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z), thr = v3(qt.x, qt.y, qt.z);

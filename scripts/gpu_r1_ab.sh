@@ -10,7 +10,7 @@ runc() { label="$1"; cfg="$2"
    | python -c "import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; print('$label', d['config']['workload'][:3], round(d['value'],1),'Msamples/s ms/step', round(d['ms_per_step'],2), 'frac', round(r['frac'],4))" >> gpurun_out/variants_ab.txt 2>&1
 }
 for rep in 1 2; do
-  for c in C2 CB C4; do
+  for c in C2 CB C1; do
     cp /tmp/new.so $L/librt_b200.so;     runc "new " $c
     cp $L/ab_prev.so $L/librt_b200.so;   runc "prev" $c
   done
