@@ -51,6 +51,12 @@ static int fail(int code, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+#define RC(call)                 \
+    do {                         \
+        int rc__ = (call);       \
+        if (rc__ != RT_OK) return rc__; \
+    } while (0)
+
 #include "rt_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -102,8 +108,11 @@ extern "C" void rt_workspace_release(int device) {
         if (device >= 0 && d != device) continue;
         Workspace &w = g_ws[d];
         std::lock_guard<std::mutex> lock(w.mu);
-        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue) continue;
         cudaSetDevice(d);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaGetLastError();
+        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue) continue;
         cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb), cudaFree(w.queue);
         w.queue = nullptr, w.queue_cap = 0;
         if (w.h_rgb) cudaFreeHost(w.h_rgb);
@@ -111,6 +120,32 @@ extern "C" void rt_workspace_release(int device) {
         w.samples = nullptr, w.accum = nullptr, w.rgb = nullptr, w.h_rgb = nullptr, w.h_accum = nullptr;
         w.samples_cap = w.accum_cap = w.rgb_cap = w.h_rgb_cap = w.h_accum_cap = 0;
     }
+}
+
+// Scene buffers come from the device's stream-ordered memory pool, configured to keep freed
+// memory (release threshold = max): a Camera.Render-style caller creates and destroys a scene per
+// frame, and cudaFree of a 17 MB texture was measured at 100-700 ms next to a multi-GiB workspace
+// (profiles/r01ah_e2e_breakdown.txt); from the pool, create + destroy cost microseconds after the
+// first frame.  rt_workspace_release() trims the pool.
+static std::once_flag g_pool_once[RT_MAX_DEVICES];
+static int scene_alloc(void **p, size_t bytes, int device, cudaStream_t st) {
+    std::call_once(g_pool_once[device], [device]() {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    });
+    CU(cudaMallocAsync(p, bytes, st));
+    return RT_OK;
+}
+template <class T>
+static int scene_alloc(T **p, size_t bytes, int device, cudaStream_t st) {
+    return scene_alloc((void **)p, bytes, device, st);
+}
+static void scene_free(void *p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,10 +274,12 @@ static int validate_desc(const rt_scene_desc *d) {
 static void free_scene(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    cudaFree(s->d_nodes), cudaFree(s->d_sph), cudaFree(s->d_mats), cudaFree(s->d_meta), cudaFree(s->d_images);
-    cudaFree(s->d_quads), cudaFree(s->d_perlins);
-    for (auto p : s->d_texels) cudaFree(p);
-    cudaFree(s->d_counter), cudaFree(s->d_stats), cudaFree(s->d_queue_count);
+    // every render call returns after its stream has drained, so nothing is still using these
+    cudaStream_t st = s->own_stream;
+    scene_free(s->d_nodes, st), scene_free(s->d_sph, st), scene_free(s->d_mats, st), scene_free(s->d_meta, st);
+    scene_free(s->d_images, st), scene_free(s->d_quads, st), scene_free(s->d_perlins, st);
+    for (auto p : s->d_texels) scene_free(p, st);
+    scene_free(s->d_counter, st), scene_free(s->d_stats, st), scene_free(s->d_queue_count, st);
     for (auto e : s->events) cudaEventDestroy(e);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -275,13 +312,13 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     pack_materials(desc, &mats);
 
     const size_t n_nodes = s->bvh.nodes.size() / 2, n_slots = s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
-    CU(cudaMalloc(&s->d_quads, std::max<size_t>(1, n_qslots) * 16 * RT_QUAD_F4));
+    RC(scene_alloc(&s->d_quads, std::max<size_t>(1, n_qslots) * 16 * RT_QUAD_F4, device, s->stream));
     if (n_qslots)
         CU(cudaMemcpyAsync(s->d_quads, s->bvh.quad.data(), n_qslots * 16 * RT_QUAD_F4, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_nodes) * 32));
-    CU(cudaMalloc(&s->d_sph, std::max<size_t>(1, n_slots) * 16));
-    CU(cudaMalloc(&s->d_meta, std::max<size_t>(1, n_slots) * 8));
-    CU(cudaMalloc(&s->d_mats, std::max<size_t>(1, mats.size()) * 16));
+    RC(scene_alloc(&s->d_nodes, std::max<size_t>(1, n_nodes) * 32, device, s->stream));
+    RC(scene_alloc(&s->d_sph, std::max<size_t>(1, n_slots) * 16, device, s->stream));
+    RC(scene_alloc(&s->d_meta, std::max<size_t>(1, n_slots) * 8, device, s->stream));
+    RC(scene_alloc(&s->d_mats, std::max<size_t>(1, mats.size()) * 16, device, s->stream));
     {
         int rc = upload_nodes(s);
         if (rc != RT_OK) return rc;
@@ -306,12 +343,12 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
             staged[i][4 * k + 2] = im.rgb16[3 * k + 2], staged[i][4 * k + 3] = 0;
         }
         uint16_t *dp = nullptr;
-        CU(cudaMalloc(&dp, n * 8));
+        RC(scene_alloc(&dp, n * 8, device, s->stream));
         s->d_texels.push_back(dp);
         CU(cudaMemcpyAsync(dp, staged[i].data(), n * 8, cudaMemcpyHostToDevice, s->stream));
         imgs[i].texels = dp;
     }
-    CU(cudaMalloc(&s->d_images, std::max<size_t>(1, imgs.size()) * sizeof(DevImage)));
+    RC(scene_alloc(&s->d_images, std::max<size_t>(1, imgs.size()) * sizeof(DevImage), device, s->stream));
     if (!imgs.empty())
         CU(cudaMemcpyAsync(s->d_images, imgs.data(), imgs.size() * sizeof(DevImage), cudaMemcpyHostToDevice, s->stream));
     // Perlin tables (materials.go:195-200) as F4 gradients + the three permutations
@@ -325,15 +362,15 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
             memcpy(pt[i].perm_x, desc->perlins[i].perm_x, 256), memcpy(pt[i].perm_y, desc->perlins[i].perm_y, 256);
             memcpy(pt[i].perm_z, desc->perlins[i].perm_z, 256);
         }
-        CU(cudaMalloc(&s->d_perlins, std::max<size_t>(1, pt.size()) * sizeof(DevPerlin)));
+        RC(scene_alloc(&s->d_perlins, std::max<size_t>(1, pt.size()) * sizeof(DevPerlin), device, s->stream));
         if (!pt.empty()) {
             CU(cudaMemcpyAsync(s->d_perlins, pt.data(), pt.size() * sizeof(DevPerlin), cudaMemcpyHostToDevice, s->stream));
             CU(cudaStreamSynchronize(s->stream)); // pt is a local
         }
     }
-    CU(cudaMalloc(&s->d_counter, sizeof(unsigned int)));
-    CU(cudaMalloc(&s->d_queue_count, RT_MAX_STAGES * sizeof(unsigned int)));
-    CU(cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long)));
+    RC(scene_alloc(&s->d_counter, sizeof(unsigned int), device, s->stream));
+    RC(scene_alloc(&s->d_queue_count, RT_MAX_STAGES * sizeof(unsigned int), device, s->stream));
+    RC(scene_alloc(&s->d_stats, 4 * sizeof(unsigned long long), device, s->stream));
     CU(cudaStreamSynchronize(s->stream));
 
     s->dev.nodes = s->d_nodes, s->dev.sph = s->d_sph, s->dev.meta = s->d_meta, s->dev.mats = s->d_mats;
