@@ -74,6 +74,30 @@ int hs_bvh_stats(const rt_scene_desc *d, int max_leaf, float origin_radius, uint
     return 0;
 }
 
+// FNV-1a over every array of the flattened BVH: the parallel build must give the same bytes for any
+// thread count (RT_B200_BVH_THREADS), and refit must not depend on it either.
+static uint64_t fnv(uint64_t h, const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+uint64_t hs_bvh_hash(const rt_scene_desc *d, int max_leaf, float origin_radius, float refit_radius) {
+    HostScene s;
+    load(d, max_leaf, origin_radius, &s);
+    if (refit_radius > 0) refit_flat_bvh(s.prims, refit_radius, &s.bvh);
+    uint64_t h = 1469598103934665603ull;
+    const FlatBvh &b = s.bvh;
+    h = fnv(h, b.nodes.data(), b.nodes.size() * sizeof(F4));
+    h = fnv(h, b.dev_nodes.data(), b.dev_nodes.size() * sizeof(F4));
+    h = fnv(h, b.sph.data(), b.sph.size() * sizeof(F4));
+    h = fnv(h, b.meta.data(), b.meta.size() * sizeof(I2));
+    h = fnv(h, b.sph_prim.data(), b.sph_prim.size() * 4);
+    h = fnv(h, b.quad.data(), b.quad.size() * sizeof(F4));
+    h = fnv(h, b.quad_prim.data(), b.quad_prim.size() * 4);
+    h = fnv(h, &b.root_ref, 4), h = fnv(h, &b.max_depth, 4), h = fnv(h, &b.pad_min, 4), h = fnv(h, &b.pad_max, 4);
+    return h;
+}
+
 int hs_trace(const rt_scene_desc *d, int max_leaf, float origin_radius, const float *origins, const float *dirs,
              int64_t n, float tmin, float tmax, int32_t *id_out, float *t_out, uint64_t *box_tests,
              uint64_t *sphere_tests) {

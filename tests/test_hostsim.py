@@ -229,3 +229,38 @@ def test_negative_and_zero_radius_spheres(hs, orc):
     rgb, acc = _hs_render(hs, s, cam, 9, cam.spp)
     rrgb, racc, _ = orc.render(s, cam, 9, order=orc.ORDER_ITERATIVE)
     assert np.array_equal(acc.view(np.uint32), racc.view(np.uint32)) and np.array_equal(rgb, rrgb)
+
+
+def bvh_hash(hs, scene, radius=0.0, refit=0.0, threads=None, max_leaf=4):
+    hs.hs_bvh_hash.restype = C.c_uint64
+    desc, keep = scene.to_desc()
+    old = os.environ.pop("RT_B200_BVH_THREADS", None)
+    if threads:
+        os.environ["RT_B200_BVH_THREADS"] = str(threads)
+    try:
+        return hs.hs_bvh_hash(C.byref(desc), max_leaf, C.c_float(radius), C.c_float(refit))
+    finally:
+        os.environ.pop("RT_B200_BVH_THREADS", None)
+        if old is not None:
+            os.environ["RT_B200_BVH_THREADS"] = old
+
+
+def test_parallel_bvh_build_is_deterministic(hs):
+    """The host build splits and emits subtrees on several threads (bvh_build.cpp); every array of the
+    flattened tree must be byte-identical for any thread count, after a refit too.  160 K spheres is above
+    both parallel thresholds (PAR_RANGE, PAR_SUBTREE)."""
+    scene = scenes.stress_scene(200)
+    ref = bvh_hash(hs, scene, 150.0, threads=1)
+    for t in (2, 3, 8, None):
+        assert bvh_hash(hs, scene, 150.0, threads=t) == ref
+    ref_refit = bvh_hash(hs, scene, 150.0, refit=300.0, threads=1)
+    assert ref_refit != ref
+    assert bvh_hash(hs, scene, 150.0, refit=300.0, threads=8) == ref_refit
+
+
+def test_bvh_layout_is_the_depth_first_build(hs, random_scene):
+    """Pins the flattened tree of the C2 scene (nodes, device nodes, slots, metadata): the hash was taken
+    from the single-threaded recursive builder that wrote the arrays in depth-first order as it went."""
+    assert bvh_hash(hs, random_scene, threads=1) == 0x145DF021C2BFCBD8
+    assert bvh_hash(hs, random_scene) == 0x145DF021C2BFCBD8
+    assert bvh_hash(hs, scenes.cornell_box_scene()) == 0xAFF672732185BF18
