@@ -1,6 +1,9 @@
 """Wall-clock breakdown of the host-buffer call sequence (create / render / destroy) for one config."""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from raytracer_go_b200 import api, scenes
 
