@@ -164,8 +164,9 @@ struct rt_scene {
     bool fixed_radius = false; // the caller gave ray_origin_radius: an envelope, never enlarged
     DevScene dev{};
     bool use_smem = false;
-    int block = 256;
-    int minb = 3;
+    int block = 512;
+    int pblock = 512;
+    int minb = 2;
     bool use_split = false; // two-stage mode: coherent primary stage + megakernel on the survivors
     unsigned int *d_queue_count = nullptr; // RT_MAX_STAGES counters, one per stage queue
     int n_stages = 1;                      // coherent stages before the megakernel (RT_B200_STAGES)
@@ -379,16 +380,26 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     s->dev.root_ref = s->bvh.root_ref;
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
     s->dev.stack_depth = s->bvh.max_depth + 2;
-    s->block = env_int("RT_B200_BLOCK", 256);
-    if (s->block != 256 && s->block != 512) s->block = 256;
-    s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 1);
+    // 512-thread CTAs, two per SM: 32 warps at 64 registers.  Measured against 256 x 3 (24 warps at 80
+    // registers): C2 +6 %, Cornell box +3 % (profiles/r01aj); the kernels wait on fixed-latency
+    // dependencies and shared-memory loads, so 8 more warps per SM buy more than 16 more registers.
+    s->block = env_int("RT_B200_BLOCK", 512);
+    if (s->block != 256 && s->block != 512) s->block = 512;
+    s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 2);
+    s->pblock = env_int("RT_B200_PBLOCK", 512); // block size of the primary stage (256 or 512)
+    if (s->pblock != 256 && s->pblock != 512) s->pblock = 512;
     {
         const char *kv = getenv("RT_B200_KERNEL");
         // default: two-stage ("split"); RT_B200_KERNEL=mega selects the one-stage megakernel
         s->use_split = kv ? std::string(kv) == "split" : true;
         s->n_stages = std::min(RT_MAX_STAGES, std::max(1, env_int("RT_B200_STAGES", 1)));
     }
-    const size_t budget = std::min<size_t>(s->smem_optin, 200 * 1024);
+    // the scene is staged in shared memory only if that still leaves room for every CTA the register
+    // budget allows (minb per SM, 1 KB reserved per CTA); a larger scene is read through L1 instead,
+    // which costs ~2 % on C2 — less than running fewer warps would
+    int smem_sm = 0;
+    CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    const size_t budget = std::min<size_t>(s->smem_optin, (size_t)smem_sm / (size_t)std::max(1, s->minb) - 1024);
     s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
                   smem_total_bytes(s->dev, s->block) <= budget;
     return RT_OK;
@@ -505,12 +516,18 @@ static int launch_split(rt_scene *s, const RenderParams &p0) {
         p.in_o = in, p.in_d = in + p.queue_stride, p.in_t = in + 2 * p.queue_stride;
         p.in_count = k ? s->d_queue_count + k - 1 : nullptr;
         p.stage_depth = k;
-        int rc = k == 0 ? launch_primary_t<256, SMEM, COUNT, QUADS, true>(s, p)
+        int rc;
+        if (s->pblock == 512)
+            rc = k == 0 ? launch_primary_t<512, SMEM, COUNT, QUADS, true>(s, p)
+                        : launch_primary_t<512, SMEM, COUNT, QUADS, false>(s, p);
+        else
+            rc = k == 0 ? launch_primary_t<256, SMEM, COUNT, QUADS, true>(s, p)
                         : launch_primary_t<256, SMEM, COUNT, QUADS, false>(s, p);
         if (rc != RT_OK) return rc;
     }
     (void)cap;
     p.stage_depth = s->n_stages; // the megakernel resumes the survivors of the last stage
+    if (s->block == 512) return launch_render_t<512, 2, SMEM, COUNT, QUADS, true>(s, p);
     return launch_render_t<256, 3, SMEM, COUNT, QUADS, true>(s, p);
 }
 
