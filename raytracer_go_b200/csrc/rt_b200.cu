@@ -381,8 +381,9 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
     s->dev.stack_depth = s->bvh.max_depth + 2;
     // 512-thread CTAs, two per SM: 32 warps at 64 registers.  Measured against 256 x 3 (24 warps at 80
-    // registers): C2 +6 %, Cornell box +3 % (profiles/r01aj); the kernels wait on fixed-latency
+    // registers): C2 +6 %, Cornell box +3 % (profiles/r01aj, r01ak); the kernels wait on fixed-latency
     // dependencies and shared-memory loads, so 8 more warps per SM buy more than 16 more registers.
+    // 640 x 2 (40 warps, 48 registers, 200 B of spills) is 6.6 % slower again (profiles/r01al).
     s->block = env_int("RT_B200_BLOCK", 512);
     if (s->block != 256 && s->block != 512) s->block = 512;
     s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 2);
