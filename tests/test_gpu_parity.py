@@ -150,6 +150,23 @@ def test_render_deterministic_and_pass_invariant(gpu, random_scene, monkeypatch)
     assert st3.kernel_launches > 3
 
 
+@pytest.mark.parametrize("env", [{"RT_B200_BLOCK": "256", "RT_B200_PBLOCK": "256"}, {"RT_B200_PBLOCK": "256"},
+                                 {"RT_B200_KERNEL": "mega"}, {"RT_B200_KERNEL": "mega", "RT_B200_BLOCK": "256"},
+                                 {"RT_B200_NO_SMEM": "1"}, {"RT_B200_STAGES": "3"}])
+def test_launch_shape_does_not_change_the_image(gpu, random_scene, monkeypatch, env):
+    """CTA shape (512 x 2 default, 256 x 3), one- / two- / multi-stage mode and the shared-memory staging are
+    scheduling choices: accumulators are bitwise those of the default configuration (the knobs are read when
+    the scene handle is created)."""
+    cam = _cam(200, 5)
+    with api.Scene(random_scene) as sc:
+        _, a0, _ = sc.render(cam, SEED, want_accum=True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with api.Scene(random_scene) as sc:
+        _, a1, _ = sc.render(cam, SEED, want_accum=True)
+    assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32))
+
+
 def test_textures_and_light(gpu, orc):
     """Image texture (with the out-of-bounds colour quirk), checker and DiffuseLight paths."""
     s = scenes.earth_scene()
