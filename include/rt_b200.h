@@ -34,7 +34,8 @@ typedef enum rt_status {
     RT_ERR_CUDA = -2,             /* a CUDA runtime call failed (message has the cudaError) */
     RT_ERR_NO_DEVICE = -3,        /* no usable sm_100 device: the library has NO CPU path   */
     RT_ERR_OUT_OF_MEMORY = -4,
-    RT_ERR_UNSUPPORTED = -5       /* e.g. a material/texture kind this build does not know  */
+    RT_ERR_UNSUPPORTED = -5,      /* e.g. a material/texture kind this build does not know  */
+    RT_ERR_INTERNAL = -6          /* a C++ exception reached the boundary (never thrown through) */
 } rt_status;
 
 /* materials.go:19-21,44-47,77-79,297-299 — the Material implementations. */

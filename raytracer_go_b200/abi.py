@@ -13,6 +13,7 @@ RT_ERR_CUDA = -2
 RT_ERR_NO_DEVICE = -3
 RT_ERR_OUT_OF_MEMORY = -4
 RT_ERR_UNSUPPORTED = -5
+RT_ERR_INTERNAL = -6
 
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT = 0, 1, 2, 3
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = 0, 1, 2, 3

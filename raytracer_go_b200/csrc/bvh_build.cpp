@@ -27,6 +27,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <system_error>
 #include <thread>
 
 namespace {
@@ -152,6 +153,17 @@ struct ThreadBudget {
     void give(int n) { idle.fetch_add(n); }
 };
 
+// Runs fn on a new thread; if the thread cannot be created (process / cgroup limits) runs it on the
+// caller instead, so a build never throws through the C ABI.
+template <class F>
+void spawn_or_run(std::vector<std::thread> &th, F fn) {
+    try {
+        th.emplace_back(fn);
+    } catch (const std::system_error &) {
+        fn();
+    }
+}
+
 struct Builder {
     const ScenePrims *prims;
     // One record per primitive, partitioned in place: every pass over a range is a linear scan
@@ -241,7 +253,7 @@ struct Builder {
         std::vector<std::thread> th;
         for (int c = 1; c < parts; c++) {
             const size_t cb_ = std::min(e, b + c * step), ce = std::min(e, cb_ + step);
-            th.emplace_back([=, &fn] { fn(cb_, ce, c); });
+            spawn_or_run(th, [=, &fn] { fn(cb_, ce, c); });
         }
         fn(b, std::min(e, b + step), 0);
         for (auto &t : th) t.join();
@@ -350,9 +362,10 @@ struct Builder {
 
         uint32_t l, r;
         if (std::min(mid - b, e - mid) >= PAR_SUBTREE && budget.take(1)) {
-            std::thread th([&] { l = split(b, mid); });
+            std::vector<std::thread> th;
+            spawn_or_run(th, [&] { l = split(b, mid); });
             r = split(mid, e);
-            th.join();
+            for (auto &t : th) t.join();
             budget.give(1);
         } else {
             l = split(b, mid);
@@ -377,9 +390,10 @@ struct Builder {
         uint32_t lref, rref;
         const uint32_t r_node = node_off + 2 + tl.n_nodes, r_sph = sph_off + tl.n_sph, r_quad = quad_off + tl.n_quad;
         if (std::min(tl.n_sph + tl.n_quad, tr.n_sph + tr.n_quad) >= PAR_SUBTREE && budget.take(1)) {
-            std::thread th([&] { lref = emit(t.left, node_off + 2, sph_off, quad_off); });
+            std::vector<std::thread> th;
+            spawn_or_run(th, [&] { lref = emit(t.left, node_off + 2, sph_off, quad_off); });
             rref = emit(t.right, r_node, r_sph, r_quad);
-            th.join();
+            for (auto &t : th) t.join();
             budget.give(1);
         } else {
             lref = emit(t.left, node_off + 2, sph_off, quad_off);
@@ -489,7 +503,7 @@ static void parallel_ranges(size_t n, int threads, F fn) {
     }
     const size_t step = (n + parts - 1) / parts;
     std::vector<std::thread> th;
-    for (int c = 1; c < parts; c++) th.emplace_back([=, &fn] { fn(std::min(n, c * step), std::min(n, (c + 1) * step)); });
+    for (int c = 1; c < parts; c++) spawn_or_run(th, [=, &fn] { fn(std::min(n, c * step), std::min(n, (c + 1) * step)); });
     fn((size_t)0, std::min(n, step));
     for (auto &t : th) t.join();
 }

@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -191,6 +193,21 @@ struct rt_scene {
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+// No exception crosses the C ABI: host allocations (scene copies, BVH build, staging buffers) and thread
+// creation can throw; the caller gets a status code and rt_last_error() instead.
+template <class F>
+static int guarded(F f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(RT_ERR_OUT_OF_MEMORY, "host memory allocation failed");
+    } catch (const std::exception &e) {
+        return fail(RT_ERR_INTERNAL, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(RT_ERR_INTERNAL, "internal error");
+    }
 }
 
 extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
@@ -406,7 +423,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     return RT_OK;
 }
 
-extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out) {
+static int rt_scene_create_impl(const rt_scene_desc *desc, int device, rt_scene **out) {
     if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "out is null");
     *out = nullptr;
     int rc = validate_desc(desc);
@@ -414,7 +431,12 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     rc = select_device(device);
     if (rc != RT_OK) return rc;
     rt_scene *s = new rt_scene();
-    rc = scene_create_impl(desc, device, s);
+    try {
+        rc = scene_create_impl(desc, device, s);
+    } catch (...) { // reported by guarded(); the half-built handle must not leak
+        free_scene(s);
+        throw;
+    }
     if (rc != RT_OK) {
         free_scene(s);
         return rc;
@@ -422,6 +444,11 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     *out = s;
     return RT_OK;
 }
+
+extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out) {
+    return guarded([&] { return rt_scene_create_impl(desc, device, out); });
+}
+
 
 extern "C" void rt_scene_destroy(rt_scene *scene) { free_scene(scene); }
 
@@ -688,7 +715,7 @@ static inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-extern "C" int rt_render_accum_device(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts,
+static int rt_render_accum_device_impl(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts,
                                       float *d_accum, rt_stats *stats) {
     if (!scene || !opts || !d_accum) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
     int rc = check_camera(camera);
@@ -711,7 +738,13 @@ extern "C" int rt_render_accum_device(rt_scene *scene, const rt_camera *camera, 
     return RT_OK;
 }
 
-extern "C" int rt_resolve_device(const float *d_accum, int32_t width, int32_t height, int32_t total_spp,
+extern "C" int rt_render_accum_device(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts,
+                                      float *d_accum, rt_stats *stats) {
+    return guarded([&] { return rt_render_accum_device_impl(scene, camera, opts, d_accum, stats); });
+}
+
+
+static int rt_resolve_device_impl(const float *d_accum, int32_t width, int32_t height, int32_t total_spp,
                                  int32_t device, void *cuda_stream, uint8_t *rgb_out) {
     if (!d_accum || !rgb_out || width < 1 || height < 1 || total_spp < 1) return fail(RT_ERR_INVALID_ARGUMENT, "bad argument");
     int rc = select_device(device);
@@ -732,7 +765,13 @@ extern "C" int rt_resolve_device(const float *d_accum, int32_t width, int32_t he
     return RT_OK;
 }
 
-extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts, uint8_t *rgb_out,
+extern "C" int rt_resolve_device(const float *d_accum, int32_t width, int32_t height, int32_t total_spp,
+                                 int32_t device, void *cuda_stream, uint8_t *rgb_out) {
+    return guarded([&] { return rt_resolve_device_impl(d_accum, width, height, total_spp, device, cuda_stream, rgb_out); });
+}
+
+
+static int rt_render_impl(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts, uint8_t *rgb_out,
                          float *accum_out, rt_stats *stats) {
     if (!scene || !opts || !rgb_out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
     int rc = check_camera(camera);
@@ -774,6 +813,12 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
     return RT_OK;
 }
 
+extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_render_opts *opts, uint8_t *rgb_out,
+                         float *accum_out, rt_stats *stats) {
+    return guarded([&] { return rt_render_impl(scene, camera, opts, rgb_out, accum_out, stats); });
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // one call, several GPUs (what a single host process such as the Go program needs)
 // ---------------------------------------------------------------------------------------------
@@ -785,7 +830,7 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
 //  * tile-split (RT_FLAG_TILE_SPLIT): device k renders scanlines k, k+n, k+2n, ... at all samples
 //    and resolves them itself; the host interleaves the rows.  No exchange between devices, and the
 //    image is bit-identical to the single-GPU render.
-extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
+static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
                                const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
                                rt_stats *stats) {
     if (!desc || !opts || !rgb_out || !devices || n_devices < 1) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
@@ -957,6 +1002,13 @@ extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camer
     return RT_OK;
 }
 
+extern "C" int rt_render_multi(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
+                               const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
+                               rt_stats *stats) {
+    return guarded([&] { return rt_render_multi_impl(desc, camera, opts, devices, n_devices, rgb_out, accum_out, stats); });
+}
+
+
 template <int BLOCK, bool QUADS>
 static int launch_trace_t(rt_scene *s, const float *d_o, const float *d_d, int64_t n, float tmin, float tmax,
                           int32_t *d_id, float *d_t) {
@@ -973,7 +1025,7 @@ static int launch_trace_t(rt_scene *s, const float *d_o, const float *d_d, int64
     return RT_OK;
 }
 
-extern "C" int rt_trace(rt_scene *scene, const float *origins, const float *dirs, int64_t n, float tmin, float tmax,
+static int rt_trace_impl(rt_scene *scene, const float *origins, const float *dirs, int64_t n, float tmin, float tmax,
                         int32_t *id_out, float *t_out) {
     if (!scene || n < 0 || (n && (!origins || !dirs || !id_out || !t_out))) return fail(RT_ERR_INVALID_ARGUMENT, "bad argument");
     if (n == 0) return RT_OK;
@@ -1008,7 +1060,13 @@ extern "C" int rt_trace(rt_scene *scene, const float *origins, const float *dirs
     return rc;
 }
 
-extern "C" int rt_primary_rays(const rt_camera *camera, const rt_render_opts *opts, int64_t pixel_begin, int64_t n_pixels,
+extern "C" int rt_trace(rt_scene *scene, const float *origins, const float *dirs, int64_t n, float tmin, float tmax,
+                        int32_t *id_out, float *t_out) {
+    return guarded([&] { return rt_trace_impl(scene, origins, dirs, n, tmin, tmax, id_out, t_out); });
+}
+
+
+static int rt_primary_rays_impl(const rt_camera *camera, const rt_render_opts *opts, int64_t pixel_begin, int64_t n_pixels,
                                float *origins_out, float *dirs_out) {
     if (!opts || !origins_out || !dirs_out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
     int rc = check_camera(camera);
@@ -1038,6 +1096,12 @@ extern "C" int rt_primary_rays(const rt_camera *camera, const rt_render_opts *op
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, "rt_primary_rays: %s", cudaGetErrorString(e));
     return RT_OK;
 }
+
+extern "C" int rt_primary_rays(const rt_camera *camera, const rt_render_opts *opts, int64_t pixel_begin, int64_t n_pixels,
+                               float *origins_out, float *dirs_out) {
+    return guarded([&] { return rt_primary_rays_impl(camera, opts, pixel_begin, n_pixels, origins_out, dirs_out); });
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // host-only helpers
@@ -1091,10 +1155,15 @@ extern "C" int rt_scene_bvh_info(const rt_scene *s, rt_bvh_info *out) {
     return RT_OK;
 }
 
-extern "C" int rt_scene_bvh_copy(const rt_scene *s, uint32_t *nodes_out, int32_t *slot_ids_out) {
+static int rt_scene_bvh_copy_impl(const rt_scene *s, uint32_t *nodes_out, int32_t *slot_ids_out) {
     if (!s) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
     if (nodes_out && !s->bvh.nodes.empty()) memcpy(nodes_out, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(F4));
     if (slot_ids_out)
         for (size_t i = 0; i < s->bvh.meta.size(); i++) slot_ids_out[i] = s->bvh.meta[i].x;
     return RT_OK;
 }
+
+extern "C" int rt_scene_bvh_copy(const rt_scene *s, uint32_t *nodes_out, int32_t *slot_ids_out) {
+    return guarded([&] { return rt_scene_bvh_copy_impl(s, nodes_out, slot_ids_out); });
+}
+
