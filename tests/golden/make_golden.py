@@ -48,7 +48,29 @@ def main():
     po, pd = orc.primary_rays(cam, 9, 400 * 100, 512, 1, 2)
     np.savez_compressed(os.path.join(HERE, "primary_rays_400.npz"), seed=9, pixel_begin=400 * 100, n_pixels=512,
                         sample_offset=1, sample_count=2, origins=po, dirs=pd, camera=np.frombuffer(bytes(cam), np.uint8))
+    # 5. the other four scenes of main.go (quads, boxes, diffuse light, Perlin noise): small renders and,
+    #    for the quad scenes, closest hits of the primary rays (Quad.Hit, hittables.go:167-194)
+    out = {}
+    for name, (sc, opts) in other_scenes().items():
+        cam = orc.camera_from_options(opts)
+        rgb, acc, st = orc.render(sc, cam, 31, order=orc.ORDER_ITERATIVE)
+        out[name + "_sha"], out[name + "_acc"], out[name + "_rgb"] = sc.sha256(), acc, rgb
+        out[name + "_rays"] = st.rays
+        if len(sc.quads):
+            ro, rd = orc.primary_rays(cam, 31, 0, cam.width * cam.height, 0, 1)
+            ids, ts = orc.trace(sc, ro, rd)
+            out[name + "_ids"], out[name + "_ts"] = ids, ts
+    np.savez_compressed(os.path.join(HERE, "render_other_scenes.npz"), **out)
     print("golden fixtures written to", HERE)
+
+
+def other_scenes():
+    return {
+        "cornell": (scenes.cornell_box_scene(), scenes.cornell_camera_options(48, 8)),
+        "quads": (scenes.quad_demo_scene(), scenes.quad_demo_camera_options(64, 4)),
+        "perlin": (scenes.perlin_demo_scene(), scenes.perlin_camera_options(64, 4)),
+        "simple_light": (scenes.simple_light_scene(), scenes.simple_light_camera_options(64, 8)),
+    }
 
 
 if __name__ == "__main__":
