@@ -6,10 +6,10 @@ profiles/experiments/r01_lane_efficiency_simulations.txt.  Run from the repo roo
 import ctypes as C, numpy as np, random, sys
 sys.path.insert(0,'/root/repo')
 from raytracer_go_b200 import scenes
-from oracle import pyoracle as orc
+from raytracer_go_b200 import api
 hs = C.CDLL('/root/repo/tests/hostsim/libhostsim.so'); hs.hs_traversal_events_rays.restype = C.c_int64
 s = scenes.random_scene(); desc, keep = s.to_desc()
-cam = orc.camera_from_options(scenes.camera_options(1200, 8))
+cam = api.camera_from_options(scenes.camera_options(1200, 8))
 N = 30_000_000; NR=400_000
 tok = np.zeros(N, np.int8); rr = np.zeros((NR,7), np.float32)
 rays=[]; meta=[]

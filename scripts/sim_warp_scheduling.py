@@ -17,12 +17,12 @@ TRACES = "/tmp/rays_events.pkl"
 
 def record_traces():
     from raytracer_go_b200 import scenes
-    from oracle import pyoracle as orc
+    from raytracer_go_b200 import api
     hs = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/hostsim/libhostsim.so"))
     hs.hs_traversal_events.restype = C.c_int64
     s = scenes.random_scene()
     desc, keep = s.to_desc()
-    cam = orc.camera_from_options(scenes.camera_options(1200, 8))
+    cam = api.camera_from_options(scenes.camera_options(1200, 8))
     n_tok = 40_000_000
     tok = np.zeros(n_tok, np.int8)
     out = []

@@ -1,4 +1,5 @@
 #!/bin/bash
+# TEST INFRASTRUCTURE (lives under tests/ because it runs the oracle as the checker): run from the repo root on a GPU box.
 # north_star check at the named size: converged 4096-spp image of the random scene at 1200x675, device vs the
 # oracle running the reference's own algorithm (random-axis BVH, recursive radiance) on an independent sample set.
 set -x
