@@ -193,6 +193,7 @@ struct Builder {
     double c_trav = 1.2; // cost of visiting a node pair, in primitive tests
     static const size_t PAR_SUBTREE = 16384; // smallest subtree worth its own thread
     static const size_t PAR_RANGE = 131072;  // smallest range whose passes are chunked over threads
+    static const uint32_t DEPTH_MEDIAN = 30; // inner-node depth from which ranges are split by count
 
     struct RangeInfo {
         Box bounds, cb;
@@ -270,7 +271,7 @@ struct Builder {
     }
 
     // phase 1: the subtree over items[b, e) as a temporary tree; returns its pool index
-    uint32_t split(size_t b, size_t e) {
+    uint32_t split(size_t b, size_t e, uint32_t depth = 0) {
         const size_t n = e - b;
         const uint32_t me = new_node();
         // helper threads in proportion to the range's share of the build, so that sibling ranges get equal help
@@ -344,7 +345,18 @@ struct Builder {
         }
 
         size_t mid;
-        if (best_axis >= 0) {
+        if (depth >= DEPTH_MEDIAN) {
+            // SAH can peel one primitive per level off a scene whose extents grow geometrically; from this
+            // depth on the ranges are halved by count along their widest axis instead, so the chain of inner
+            // nodes stays below DEPTH_MEDIAN + 32 <= the kernels' traversal stack (RT_LOCAL_STACK)
+            int ax = 0;
+            for (int k = 1; k < 3; k++)
+                if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+            mid = b + n / 2;
+            std::nth_element(items.begin() + b, items.begin() + mid, items.begin() + e, [ax](const Prim &x, const Prim &y) {
+                return x.c[ax] < y.c[ax] || (x.c[ax] == y.c[ax] && x.g < y.g);
+            });
+        } else if (best_axis >= 0) {
             float lo = cb.lo[best_axis], ext = cb.hi[best_axis] - cb.lo[best_axis];
             float scale = (float)nbins / ext;
             auto it = std::partition(items.begin() + b, items.begin() + e, [&](const Prim &q) {
@@ -363,13 +375,13 @@ struct Builder {
         uint32_t l, r;
         if (std::min(mid - b, e - mid) >= PAR_SUBTREE && budget.take(1)) {
             std::vector<std::thread> th;
-            spawn_or_run(th, [&] { l = split(b, mid); });
-            r = split(mid, e);
+            spawn_or_run(th, [&] { l = split(b, mid, depth + 1); });
+            r = split(mid, e, depth + 1);
             for (auto &t : th) t.join();
             budget.give(1);
         } else {
-            l = split(b, mid);
-            r = split(mid, e);
+            l = split(b, mid, depth + 1);
+            r = split(mid, e, depth + 1);
         }
         TNode &tt = pool[me]; // (the pool never reallocates)
         const TNode &tl = pool[l], &tr = pool[r];

@@ -397,6 +397,8 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     s->dev.root_ref = s->bvh.root_ref;
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
     s->dev.stack_depth = s->bvh.max_depth + 2;
+    if (s->dev.stack_depth > RT_LOCAL_STACK) // cannot happen: the builder balances the tree below depth 30
+        return fail(RT_ERR_INTERNAL, "BVH depth %u exceeds the traversal stack (%d)", s->bvh.max_depth, RT_LOCAL_STACK);
     // 512-thread CTAs, two per SM: 32 warps at 64 registers.  Measured against 256 x 3 (24 warps at 80
     // registers): C2 +6 %, Cornell box +3 % (profiles/r01aj, r01ak); the kernels wait on fixed-latency
     // dependencies and shared-memory loads, so 8 more warps per SM buy more than 16 more registers.

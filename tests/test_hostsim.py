@@ -264,3 +264,38 @@ def test_bvh_layout_is_the_depth_first_build(hs, random_scene):
     assert bvh_hash(hs, random_scene, threads=1) == 0x145DF021C2BFCBD8
     assert bvh_hash(hs, random_scene) == 0x145DF021C2BFCBD8
     assert bvh_hash(hs, scenes.cornell_box_scene()) == 0xAFF672732185BF18
+
+
+def geometric_scene(n=240, ratio=1.3):
+    """Spheres whose positions and radii grow geometrically: binned SAH peels one of them off per level."""
+    tex = np.zeros(1, scenes.TEXTURE_DT)
+    mat = np.zeros(1, scenes.MATERIAL_DT)
+    sph = np.zeros(n, scenes.SPHERE_DT)
+    x = ratio ** np.arange(n, dtype=np.float64)
+    sph["cx"], sph["cy"], sph["cz"] = x, 0.1 * x, -0.05 * x
+    sph["r"] = 0.1 * x
+    return scenes.SceneData(sph, mat, tex, ray_origin_radius=1.0, name="geometric")
+
+
+def test_bvh_depth_stays_within_the_traversal_stack(hs, orc):
+    """A scene that would make a pure SAH tree one level deep per primitive: below inner depth 30 the builder
+    halves ranges by count, so the chain of inner nodes fits the kernels' 64-entry traversal stack, and the
+    traversal still returns World.Hit's answer."""
+    s = geometric_scene()
+    desc, keep = s.to_desc()
+    nn, ns, md, p0, p1 = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_float(), C.c_float()
+    hs.hs_bvh_stats(C.byref(desc), 1, C.c_float(1.0), C.byref(nn), C.byref(ns), C.byref(md), C.byref(p0), C.byref(p1))
+    assert ns.value == len(s.spheres)
+    assert 30 < md.value <= 62, md.value
+    rng = np.random.default_rng(3)
+    n = 20000
+    pick = rng.integers(0, len(s.spheres), n)
+    c = np.stack([s.spheres["cx"][pick], s.spheres["cy"][pick], s.spheres["cz"][pick]], -1).astype(np.float64)
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    o = (c + v * (s.spheres["r"][pick] * 1.0000001)[:, None]).astype(np.float32)  # on the surfaces
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    ids, ts, _, _ = hs_trace(hs, s, o, d, max_leaf=1, radius=1.0)
+    rids, rts = orc.trace(s, o, d)
+    near = (rids < 0) | (rts < 1e3)  # inside the envelope the padding is exact for
+    assert np.array_equal(ids[near], rids[near])
