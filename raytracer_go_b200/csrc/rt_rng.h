@@ -20,7 +20,8 @@
 #include "rt_math.h"
 
 struct RngBlock {
-    float u0, u1, u2, u3;
+    float u0, u1, u2, u3;    // Float32() of the four words
+    uint32_t w0, w1, w2, w3; // the words themselves (for the fused mappings below)
 };
 
 // The ten round keys (k0 + r*W0, k1 + r*W1) depend on the seed only.  On the device they live in
@@ -76,19 +77,26 @@ struct PathRng {
         block++;
         RngBlock b;
         b.u0 = to_f32(c0), b.u1 = to_f32(c1), b.u2 = to_f32(c2), b.u3 = to_f32(c3);
+        b.w0 = c0, b.w1 = c1, b.w2 = c2, b.w3 = c3;
         return b;
     }
 };
 
 // math.go:30-32: min + r*(max-min)
 RT_HD float rand_range(float r, float lo, float hi) { return lo + r * (hi - lo); }
+// rand_range(Float32(), -1, 1) and -0.5 + Float32() straight from a Philox word.  Float32() is k * 2^-24 with
+// k < 2^24 (exact), and so are r * 2 and k * 2^-23: the reference's "multiply, then add" rounds once, at the add,
+// and the fused multiply-add below rounds the same real number once — identical bits, one instruction instead
+// of three (the oracle keeps the unfused form; the parity tests compare the two).
+RT_HD float rand_pm1(uint32_t w) { return fmaf((float)(w >> 8), 1.0f / 8388608.0f, -1.0f); }
+RT_HD float rand_centered(uint32_t w) { return fmaf((float)(w >> 8), 1.0f / 16777216.0f, -0.5f); }
 
 // vec3.go:182-190 (NewVec3UnitRandOnUnitSphere32): cube rejection, then Unit(); one block per trial
 RT_HD V3 rand_unit(PathRng &rng) {
     V3 v;
     for (;;) {
         const RngBlock b = rng.next();
-        v = v3(rand_range(b.u0, -1.0f, 1.0f), rand_range(b.u1, -1.0f, 1.0f), rand_range(b.u2, -1.0f, 1.0f));
+        v = v3(rand_pm1(b.w0), rand_pm1(b.w1), rand_pm1(b.w2));
         if (lensq(v) < 1.0f) break;
     }
     return unit(v); // after the loop: the sqrt and divide run once, with the lanes reconverged

@@ -75,15 +75,15 @@ RT_HD void generate_ray(const DevCamera &c, PathRng &rng, int i, int j, V3 &orig
     pc = pc + du_off;
     pc = pc + dv_off;
     RngBlock b = rng.next();
-    float dx = -0.5f + b.u0;
-    float dy = -0.5f + b.u1;
+    float dx = rand_centered(b.w0); // -0.5 + Float32(), camera.go:290
+    float dy = rand_centered(b.w1);
     pc = pc + (c.du * dx + c.dv * dy);
-    float sx = rand_range(b.u2, -1.0f, 1.0f), sy = rand_range(b.u3, -1.0f, 1.0f);
+    float sx = rand_pm1(b.w2), sy = rand_pm1(b.w3);
     while (!(sx * sx + sy * sy + 0.0f * 0.0f < 1.0f)) {
         b = rng.next();
-        sx = rand_range(b.u0, -1.0f, 1.0f), sy = rand_range(b.u1, -1.0f, 1.0f);
+        sx = rand_pm1(b.w0), sy = rand_pm1(b.w1);
         if (sx * sx + sy * sy + 0.0f * 0.0f < 1.0f) break;
-        sx = rand_range(b.u2, -1.0f, 1.0f), sy = rand_range(b.u3, -1.0f, 1.0f);
+        sx = rand_pm1(b.w2), sy = rand_pm1(b.w3);
     }
     origin = c.center;
     if (c.defocus) origin = c.center + (c.disk_u * sx + c.disk_v * sy);

@@ -299,3 +299,17 @@ def test_bvh_depth_stays_within_the_traversal_stack(hs, orc):
     rids, rts = orc.trace(s, o, d)
     near = (rids < 0) | (rts < 1e3)  # inside the envelope the padding is exact for
     assert np.array_equal(ids[near], rids[near])
+
+
+def test_fused_range_mappings_are_exact():
+    """rt_rng.h maps a Philox word to [-1, 1) / [-0.5, 0.5) with ONE fused multiply-add where the reference
+    multiplies and then adds (math.go:30-32, camera.go:290): every product involved is exact (k * 2^-24 with
+    k < 2^24, times 2), so both round the same real number once.  All 2^24 values of k, bit for bit."""
+    k = np.arange(1 << 24, dtype=np.uint32)
+    r = k.astype(np.float32) * np.float32(2.0 ** -24)                      # Float32()
+    ref = np.float32(-1.0) + r * (np.float32(1.0) - np.float32(-1.0))     # lo + r * (hi - lo), unfused float32
+    fused = (k.astype(np.float64) * 2.0 ** -23 - 1.0).astype(np.float32)  # fmaf: exact product, one rounding
+    assert np.array_equal(ref.view(np.uint32), fused.view(np.uint32))
+    ref = np.float32(-0.5) + r
+    fused = (k.astype(np.float64) * 2.0 ** -24 - 0.5).astype(np.float32)
+    assert np.array_equal(ref.view(np.uint32), fused.view(np.uint32))
