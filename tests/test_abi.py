@@ -103,3 +103,27 @@ def test_non_finite_geometry_is_rejected(rtlib):
     desc, keep = m.to_desc()
     rc = rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h))
     assert rc in (abi.RT_ERR_INVALID_ARGUMENT, abi.RT_ERR_NO_DEVICE)   # the id check needs the device selected first
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the
+    contract's keys on rank 0, nothing and exit 0 on the other ranks of a torchrun launch."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--width", "64", "--spp", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Msamples/s" and d["unit"] == "Msamples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("C2")
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29871")
+    out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
