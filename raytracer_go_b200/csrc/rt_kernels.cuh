@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
         stack.stride = BLOCK;
     }
     const unsigned lane = threadIdx.x & 31u;
+    __shared__ uint32_t cta_count[BLOCK / 32], cta_base[BLOCK / 32];
     unsigned long long n_rays = 0, n_hits = 0;
     WorkCounters wc;
     wc.box_tests = wc.sphere_tests = 0;
@@ -353,18 +354,44 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
             carries = survive && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f);
             if (!survive || carries) p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
         }
-        // append survivors: one atomic per warp, consecutive entries for consecutive lanes
+        // append survivors, consecutive entries for consecutive lanes
         const unsigned m = __ballot_sync(0xffffffffu, survive);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(p.queue_count, (unsigned)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (survive) {
-                const uint32_t e = base + __popc(m & ((1u << lane) - 1u));
-                p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
-                p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block));
-                p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, carries ? 1.0f : 0.0f);
+        uint32_t first_entry = 0;
+        if constexpr (SMEM) { // one atomic per warp
+            if (m) {
+                if (lane == (unsigned)(__ffs(m) - 1)) first_entry = atomicAdd(p.queue_count, (unsigned)__popc(m));
+                first_entry = __shfl_sync(0xffffffffu, first_entry, __ffs(m) - 1);
             }
+        } else {
+            // Scene in global memory (1 M spheres): one atomic per CTA and round, behind two barriers.  The
+            // barriers keep the CTA's warps on neighbouring pixels, which the L1-resident top of the tree likes
+            // (C4 +5.5 %); with the scene in shared memory they only add waiting (C2 -1 %), hence the split.
+            // The round count is the same for every thread of the grid, so the barriers are reached by all.
+            const unsigned warp = threadIdx.x >> 5;
+            if (lane == 0) cta_count[warp] = (uint32_t)__popc(m);
+            __syncthreads();
+            if (warp == 0) { // exclusive prefix over the warps' counts, then the CTA's reservation
+                const uint32_t c = lane < BLOCK / 32 ? cta_count[lane] : 0u;
+                uint32_t incl = c;
+#pragma unroll
+                for (int off = 1; off < BLOCK / 32; off <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+                    if ((int)lane >= off) incl += up;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, BLOCK / 32 - 1);
+                uint32_t base = 0;
+                if (lane == 0 && total) base = atomicAdd(p.queue_count, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lane < BLOCK / 32) cta_base[lane] = base + incl - c;
+            }
+            __syncthreads();
+            first_entry = cta_base[warp];
+        }
+        if (survive) {
+            const uint32_t e = first_entry + __popc(m & ((1u << lane) - 1u));
+            p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
+            p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block));
+            p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, carries ? 1.0f : 0.0f);
         }
     }
     unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
