@@ -173,7 +173,7 @@ struct Builder {
         float c[3]; // centre
         uint32_t g; // global primitive index
     };
-    std::vector<Prim> items;
+    RawVec<Prim> items;
     FlatBvh *out;
     int max_leaf;
     std::unique_ptr<TNode[]> pool; // uninitialised; nodes are handed out in per-thread blocks
@@ -545,7 +545,7 @@ static void make_device_nodes(FlatBvh *bvh) {
     });
 }
 
-void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out) {
+void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out, const double *center) {
     *out = FlatBvh();
     const size_t n = prims.size();
     if (n == 0) return;
@@ -565,7 +565,10 @@ void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, 
         fprintf(stderr, "[bvh] %-14s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     };
-    compute_scene_center(prims, m, &ext);
+    if (center)
+        m[0] = center[0], m[1] = center[1], m[2] = center[2];
+    else
+        compute_scene_center(prims, m, &ext);
     lap("scene centre");
     std::vector<float> part_min(threads + 1, POS_INF), part_max(threads + 1, 0.0f);
     std::atomic<int> part_next{0};

@@ -3,6 +3,9 @@
 #define RT_BVH_BUILD_H
 
 #include <cstdint>
+#include <memory>
+#include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/rt_b200.h"
@@ -17,22 +20,42 @@ struct ScenePrims {
     size_t size() const { return spheres.size() + quads.size(); }
 };
 
+// std::allocator that leaves trivially constructible elements uninitialised on resize(): the builder
+// writes every element of these arrays itself, and zero-filling 70 MB first cost 18 ms of a 1 M-sphere build.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        typedef NoInitAlloc<U> other;
+    };
+    NoInitAlloc() = default;
+    template <class U>
+    NoInitAlloc(const NoInitAlloc<U> &) {}
+    template <class U>
+    void construct(U *p) { ::new ((void *)p) U; } // default-initialisation: no zero fill
+    template <class U, class... A>
+    void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+template <class T>
+using RawVec = std::vector<T, NoInitAlloc<T>>;
+
 struct FlatBvh {
-    std::vector<F4> nodes;          // 2 x F4 per node (min.xyz, ref)(max.xyz, 0), siblings adjacent, depth-first order
-    std::vector<F4> dev_nodes;      // the same nodes as the kernels read them: (centre.xyz, ref)(half-extent.xyz, 0),
-                                    // [c - h, c + h] encloses [min, max] (box_test in rt_trace.h)
-    std::vector<F4> sph;            // per sphere slot: centre, radius
-    std::vector<I2> meta;           // per sphere slot: object ID, material index
-    std::vector<uint32_t> sph_prim; // per sphere slot: index into ScenePrims.spheres
-    std::vector<F4> quad;           // per quad slot: RT_QUAD_F4 x F4 (layout in rt_trace.h)
-    std::vector<uint32_t> quad_prim; // per quad slot: index into ScenePrims.quads
+    RawVec<F4> nodes;          // 2 x F4 per node (min.xyz, ref)(max.xyz, 0), siblings adjacent, depth-first order
+    RawVec<F4> dev_nodes;      // the same nodes as the kernels read them: (centre.xyz, ref)(half-extent.xyz, 0),
+                               // [c - h, c + h] encloses [min, max] (box_test in rt_trace.h)
+    RawVec<F4> sph;            // per sphere slot: centre, radius
+    RawVec<I2> meta;           // per sphere slot: object ID, material index
+    RawVec<uint32_t> sph_prim; // per sphere slot: index into ScenePrims.spheres
+    RawVec<F4> quad;           // per quad slot: RT_QUAD_F4 x F4 (layout in rt_trace.h)
+    RawVec<uint32_t> quad_prim; // per quad slot: index into ScenePrims.quads
     uint32_t root_ref = RT_REF_NONE;
     uint32_t max_depth = 0;         // deepest chain of inner nodes (bounds the traversal stack)
     float pad_min = 0, pad_max = 0; // smallest / largest box padding applied to a primitive
 };
 
 // max_leaf in [1, RT_MAX_LEAF].  origin_radius: rt_scene_desc.ray_origin_radius (0 = derive).
-void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out);
+// `center` (optional): compute_scene_center's m, if the caller has it already.
+void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out, const double *center = nullptr);
 // Recompute all boxes for a (larger) origin radius; topology and slot order are unchanged.
 void refit_flat_bvh(const ScenePrims &prims, float origin_radius, FlatBvh *bvh);
 // Per-axis median m of the primitive centres, the 90th percentile of |c - m| + extent, and

@@ -318,16 +318,28 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     s->stream = s->own_stream;
 
+    const bool timing = getenv("RT_B200_BVH_TIMING") != nullptr; // host-side phases of a scene creation
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[scene] %-14s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     if (!load_scene_prims(desc, &s->prims))
         return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
+    lap("copy prims");
     s->has_quads = !s->prims.quads.empty();
     compute_scene_center(s->prims, s->center, &s->extent90, &s->surface_extent);
     s->fixed_radius = desc->ray_origin_radius > 0;
     s->origin_radius = s->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
-    build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh);
+    lap("scene centre");
+    build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh, s->center);
+    lap("bvh build");
 
     std::vector<F4> mats;
     pack_materials(desc, &mats);
+    lap("materials");
 
     const size_t n_nodes = s->bvh.nodes.size() / 2, n_slots = s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
     RC(scene_alloc(&s->d_quads, std::max<size_t>(1, n_qslots) * 16 * RT_QUAD_F4, device, s->stream));
@@ -422,6 +434,8 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     const size_t budget = std::min<size_t>(s->smem_optin, (size_t)smem_sm / (size_t)std::max(1, s->minb) - 1024);
     s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
                   smem_total_bytes(s->dev, s->block) <= budget;
+    if (timing) CU(cudaStreamSynchronize(s->stream));
+    lap("alloc + upload");
     return RT_OK;
 }
 
