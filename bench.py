@@ -333,16 +333,16 @@ def main():
         "achieved": achieved, "peak": peak_instr,
         "unit": "T lane-instr/s", "frac": achieved / peak_instr,
         # dram__bytes_read.sum + dram__bytes_write.sum of one C2 pass (66.42 M paths = 82 spp x 810 000 px):
-        # primary_stage_kernel 2.784 GB + render_kernel<SPLIT> 3.599 GB, ncu --set full,
-        # profiles/r01am_kernels_ncu_full.txt.  Algorithmic: a 16-byte radiance record per path plus a
+        # primary_stage_kernel 2.784 GB + render_kernel<SPLIT> 3.596 GB, ncu --set full,
+        # profiles/r01bc_kernels_ncu_full.txt.  Algorithmic: a 16-byte radiance record per path plus a
         # 48-byte queue entry written and read once per path that survives its first segment (83 %).
-        "traffic": 6.383e9 * samples_per_launch / 66.42e6
+        "traffic": 6.380e9 * samples_per_launch / 66.42e6
         if args.config == "C2" and not args.width else None,
         "traffic_detail": {"unit": "bytes of DRAM traffic per pass (both kernels), scaled from the profiled 66.42 M-path pass "
                                    "to this run's average pass size",
-                           "profiled_bytes": 6.383e9, "profiled_paths": 66.42e6,
+                           "profiled_bytes": 6.380e9, "profiled_paths": 66.42e6,
                            "algorithmic_bytes": (16 + 96 * 0.83) * samples_per_launch,
-                           "source": "profiles/r01am_kernels_ncu_full.txt (C2 pass: 82 spp x 1200x675 = 66.42 M paths)"},
+                           "source": "profiles/r01bc_kernels_ncu_full.txt (C2 pass: 82 spp x 1200x675 = 66.42 M paths)"},
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz {peaks['sm_max_mhz']:.0f} ({peak_src} MEASURED_PEAKS.json clock)",
         "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": n_box,
         "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit, "counted_at_spp": cnt_spp,
