@@ -187,6 +187,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # every rank builds its own BVH on the host: share the box's cores instead of oversubscribing them
+    os.environ.setdefault("RT_B200_BVH_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, world)))))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":

@@ -309,7 +309,27 @@ static int upload_nodes(rt_scene *s) {
     return RT_OK;
 }
 
-static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s) {
+// The device-independent half of a scene: copies of the hittables, the scene's centre / extent, the
+// flattened BVH.  rt_render_multi builds it once and hands it to every device's scene_create_impl instead
+// of letting N host threads build the same tree N times.
+struct HostSceneParts {
+    ScenePrims prims;
+    double center[3] = {0, 0, 0}, extent90 = 0, surface_extent = 0;
+    float origin_radius = 0;
+    bool fixed_radius = false;
+    FlatBvh bvh;
+};
+static int host_scene_parts(const rt_scene_desc *desc, HostSceneParts *h) {
+    if (!load_scene_prims(desc, &h->prims))
+        return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
+    compute_scene_center(h->prims, h->center, &h->extent90, &h->surface_extent);
+    h->fixed_radius = desc->ray_origin_radius > 0;
+    h->origin_radius = h->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * h->extent90);
+    build_flat_bvh(h->prims, h->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &h->bvh, h->center);
+    return RT_OK;
+}
+
+static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s, const HostSceneParts *pre = nullptr) {
     s->device = device;
     CU(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
     int optin = 0;
@@ -326,16 +346,25 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
         fprintf(stderr, "[scene] %-14s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     };
-    if (!load_scene_prims(desc, &s->prims))
-        return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
-    lap("copy prims");
-    s->has_quads = !s->prims.quads.empty();
-    compute_scene_center(s->prims, s->center, &s->extent90, &s->surface_extent);
-    s->fixed_radius = desc->ray_origin_radius > 0;
-    s->origin_radius = s->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
-    lap("scene centre");
-    build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh, s->center);
-    lap("bvh build");
+    if (pre) { // built once by the caller (rt_render_multi); every handle keeps its own copy (refits are per handle)
+        s->prims = pre->prims, s->bvh = pre->bvh;
+        s->center[0] = pre->center[0], s->center[1] = pre->center[1], s->center[2] = pre->center[2];
+        s->extent90 = pre->extent90, s->surface_extent = pre->surface_extent;
+        s->fixed_radius = pre->fixed_radius, s->origin_radius = pre->origin_radius;
+        s->has_quads = !s->prims.quads.empty();
+        lap("copy parts");
+    } else {
+        if (!load_scene_prims(desc, &s->prims))
+            return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
+        lap("copy prims");
+        s->has_quads = !s->prims.quads.empty();
+        compute_scene_center(s->prims, s->center, &s->extent90, &s->surface_extent);
+        s->fixed_radius = desc->ray_origin_radius > 0;
+        s->origin_radius = s->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
+        lap("scene centre");
+        build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh, s->center);
+        lap("bvh build");
+    }
 
     std::vector<F4> mats;
     pack_materials(desc, &mats);
@@ -439,7 +468,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s)
     return RT_OK;
 }
 
-static int rt_scene_create_impl(const rt_scene_desc *desc, int device, rt_scene **out) {
+static int rt_scene_create_impl(const rt_scene_desc *desc, int device, rt_scene **out, const HostSceneParts *pre = nullptr) {
     if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "out is null");
     *out = nullptr;
     int rc = validate_desc(desc);
@@ -448,7 +477,7 @@ static int rt_scene_create_impl(const rt_scene_desc *desc, int device, rt_scene 
     if (rc != RT_OK) return rc;
     rt_scene *s = new rt_scene();
     try {
-        rc = scene_create_impl(desc, device, s);
+        rc = scene_create_impl(desc, device, s, pre);
     } catch (...) { // reported by guarded(); the half-built handle must not leak
         free_scene(s);
         throw;
@@ -889,7 +918,21 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
     };
     std::vector<Job> jobs(n_devices);
     const int base = spp / n_devices, rem = spp % n_devices;
-    std::vector<std::thread> threads;
+    // the BVH is built once, here, and copied into every device's handle
+    rc = validate_desc(desc);
+    if (rc != RT_OK) return rc;
+    HostSceneParts parts;
+    rc = host_scene_parts(desc, &parts);
+    if (rc != RT_OK) return rc;
+    // a device thread that cannot be started joins the ones that were before the error is reported
+    struct Joiner {
+        std::vector<std::thread> v;
+        ~Joiner() {
+            for (auto &t : v)
+                if (t.joinable()) t.join();
+        }
+    } joiner;
+    std::vector<std::thread> &threads = joiner.v;
     for (int k = 0; k < n_devices; k++) {
         Job &j = jobs[k];
         j.o = *opts;
@@ -911,7 +954,7 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
         threads.emplace_back([&, k]() {
             Job &jj = jobs[k];
             if (jj.idle) return;
-            jj.rc = rt_scene_create(desc, devs[k], &jj.scene);
+            jj.rc = guarded([&] { return rt_scene_create_impl(desc, devs[k], &jj.scene, &parts); });
             if (jj.rc == RT_OK) {
                 Workspace &ws = g_ws[devs[k]];
                 const size_t my_acc = (size_t)jj.o.row_count * row_bytes;
