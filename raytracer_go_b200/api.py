@@ -423,6 +423,28 @@ class Camera:
         writer.write(rgb.tobytes())
         return None
 
+    def RenderPNG(self, world, writer):
+        """PNG (the other half of the reference's TODO at camera.go:196).  `writer` takes bytes."""
+        with Scene(flatten_world(world), self.device) as sc:
+            rgb, _, self.last_stats = sc.render(self.c, self.seed)
+        writer.write(encode_png(rgb))
+        return None
+
+
+def encode_png(rgb):
+    """RGB8 (h, w, 3) -> PNG bytes: 8-bit truecolour, filter 0 on every scanline, one zlib stream."""
+    import struct
+    import zlib
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    h, w, _ = rgb.shape
+    raw = np.concatenate([np.zeros((h, 1), np.uint8), rgb.reshape(h, w * 3)], axis=1).tobytes()
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
+            chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
 
 def NewCamera(aspectRatio, imageWidth, *opts, seed=scenes.RENDER_SEED, device=0):
     """camera.go:104-126 with its defaults."""

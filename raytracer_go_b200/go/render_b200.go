@@ -32,6 +32,7 @@ import "C"
 import (
 	"fmt"
 	"image"
+	"image/png"
 	"io"
 	"strconv"
 	"strings"
@@ -50,6 +51,8 @@ type B200Options struct {
 	// Binary writes a P6 PPM (3 bytes per pixel) instead of the reference's P3 text — the TODO at
 	// camera.go:196; a 3840x2160 frame is 24.9 MB instead of ~100 MB of text.
 	Binary bool
+	// PNG writes a PNG through the standard library's encoder instead (takes precedence over Binary).
+	PNG bool
 }
 
 type b200Flat struct {
@@ -332,6 +335,13 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 		}
 	}
 
+	if o.PNG {
+		img := image.NewNRGBA(image.Rect(0, 0, w, h))
+		for p := 0; p < w*h; p++ {
+			img.Pix[4*p], img.Pix[4*p+1], img.Pix[4*p+2], img.Pix[4*p+3] = rgb[3*p], rgb[3*p+1], rgb[3*p+2], 255
+		}
+		return png.Encode(writer, img)
+	}
 	if o.Binary {
 		if _, err := io.WriteString(writer, "P6\n"+strconv.Itoa(w)+" "+strconv.Itoa(h)+"\n255\n"); err != nil {
 			return err

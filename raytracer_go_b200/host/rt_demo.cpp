@@ -3,6 +3,7 @@
 // the reference's out/img.ppm.
 //   rt_demo [width=400] [spp=500] [out=out/img.ppm] [scene_seed=0x5EED0001]      random spheres
 //   rt_demo cornell [width=600] [spp=200] [out=out/img.ppm]                       Cornell box
+// (an `out` ending in .png is written as PNG)
 // The reference seeds its scene RNG from the clock (main.go:246); here a fixed-seed SplitMix64
 // supplies rand.Float32() so runs are reproducible.
 #include <chrono>
@@ -25,6 +26,12 @@ struct Rand {
     }
 };
 
+// an output path ending in .png selects the PNG writer, anything else the reference's P3 text
+static bool ends_with_png(const char *path) {
+    const std::string p(path);
+    return p.size() >= 4 && p.compare(p.size() - 4, 4, ".png") == 0;
+}
+
 static int cornell(int argc, char **argv) { // main.go:194-225
     const int width = argc > 2 ? atoi(argv[2]) : 600;
     const int spp = argc > 3 ? atoi(argv[3]) : 200;
@@ -46,9 +53,9 @@ static int cornell(int argc, char **argv) { // main.go:194-225
     world->Add(NewQuad(NewVec3(0, 0, 555), NewVec3(555, 0, 0), NewVec3(0, 555, 0), white));
     world->Add(Box(NewVec3(130, 0, 65), NewVec3(295, 165, 230), white));
     world->Add(Box(NewVec3(265, 0, 295), NewVec3(430, 330, 460), white));
-    std::ofstream f(out);
+    std::ofstream f(out, std::ios::binary);
     if (!f) return fprintf(stderr, "cannot open %s\n", out), 2;
-    std::string err = camera->Render(NewBVHFromWorld(world), f);
+    std::string err = camera->Render(NewBVHFromWorld(world), f, false, ends_with_png(out));
     if (!err.empty()) return fprintf(stderr, "render failed: %s\n", err.c_str()), 1;
     const rt_stats &st = camera->last_stats;
     printf("Finished: cornell box %dx%d, %d spp: %.1f Msamples/s device, %.1f Mrays/s\n", camera->c.width,
@@ -98,12 +105,12 @@ int main(int argc, char **argv) {
     world->Add(NewSphere(NewVec3(4, 1, 0), 1, NewMetal(NewVec3(0.7f, 0.6f, 0.5f), 0)));
     auto tree = NewBVHFromWorld(world);
 
-    std::ofstream f(out);
+    std::ofstream f(out, std::ios::binary);
     if (!f) {
         fprintf(stderr, "cannot open %s\n", out);
         return 2;
     }
-    std::string err = camera->Render(tree, f);
+    std::string err = camera->Render(tree, f, false, ends_with_png(out));
     if (!err.empty()) { // main.go:74-76 panics; a CLI reports and exits non-zero
         fprintf(stderr, "render failed: %s\n", err.c_str());
         return 1;

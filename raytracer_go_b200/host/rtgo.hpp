@@ -186,6 +186,65 @@ inline CameraOpt WithDefocusAngleDegrees(float d) { return [=](rt_camera_options
 inline CameraOpt WithFocusDist(float d) { return [=](rt_camera_options &o) { o.focus_dist = d; }; }
 inline CameraOpt WithBackgroundColor(Vec3 c) { return [=](rt_camera_options &o) { o.background[0] = c.X, o.background[1] = c.Y, o.background[2] = c.Z; }; }
 
+// PNG without a compression library: 8-bit truecolour, filter 0, the zlib stream made of stored
+// (uncompressed) deflate blocks — a valid PNG every decoder reads, 3 bytes per pixel + 0.01 % framing.
+inline void write_png(std::ostream &out, const uint8_t *rgb, int w, int h) {
+    static uint32_t table[256];
+    static bool have_table = false;
+    if (!have_table) {
+        for (uint32_t n = 0; n < 256; n++) {
+            uint32_t c = n;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[n] = c;
+        }
+        have_table = true;
+    }
+    auto be32 = [](std::string &s, uint32_t v) {
+        s.push_back((char)(v >> 24)), s.push_back((char)(v >> 16)), s.push_back((char)(v >> 8)), s.push_back((char)v);
+    };
+    auto chunk = [&](const char *tag, const std::string &data) {
+        std::string c;
+        be32(c, (uint32_t)data.size());
+        c.append(tag, 4);
+        c += data;
+        uint32_t crc = 0xFFFFFFFFu;
+        for (size_t i = 4; i < c.size(); i++) crc = table[(crc ^ (uint8_t)c[i]) & 0xFF] ^ (crc >> 8);
+        be32(c, crc ^ 0xFFFFFFFFu);
+        out.write(c.data(), (std::streamsize)c.size());
+    };
+    out.write("\x89PNG\r\n\x1a\n", 8);
+    std::string ihdr;
+    be32(ihdr, (uint32_t)w), be32(ihdr, (uint32_t)h);
+    ihdr += std::string("\x08\x02\x00\x00\x00", 5); // 8 bits, colour type 2 (RGB), deflate, filter 0, no interlace
+    chunk("IHDR", ihdr);
+    // raw image data: a filter byte (0) in front of every scanline
+    std::string raw;
+    raw.reserve((size_t)h * ((size_t)w * 3 + 1));
+    for (int j = 0; j < h; j++) {
+        raw.push_back('\0');
+        raw.append(reinterpret_cast<const char *>(rgb) + (size_t)j * w * 3, (size_t)w * 3);
+    }
+    std::string z("\x78\x01", 2); // zlib header: deflate, 32 K window, no preset dictionary
+    uint32_t a = 1, b = 0;         // adler32 of the raw data
+    for (size_t pos = 0; pos < raw.size() || pos == 0;) {
+        const size_t n = std::min<size_t>(65535, raw.size() - pos);
+        const bool last = pos + n >= raw.size();
+        z.push_back(last ? '\x01' : '\x00'); // stored block, BFINAL on the last one
+        z.push_back((char)(n & 0xFF)), z.push_back((char)(n >> 8));
+        z.push_back((char)(~n & 0xFF)), z.push_back((char)((~n >> 8) & 0xFF));
+        z.append(raw, pos, n);
+        for (size_t i = pos; i < pos + n; i++) {
+            a = (a + (uint8_t)raw[i]) % 65521u;
+            b = (b + a) % 65521u;
+        }
+        pos += n;
+        if (last) break;
+    }
+    be32(z, (b << 16) | a);
+    chunk("IDAT", z);
+    chunk("IEND", std::string());
+}
+
 struct Camera {
     rt_camera_options options{};
     rt_camera c{};
@@ -195,7 +254,7 @@ struct Camera {
 
     // camera.go:180: returns "" for Go's nil error, the message otherwise.  binary = false writes the
     // reference's P3 text; binary = true writes P6 (the reference's TODO at camera.go:196).
-    std::string Render(const std::shared_ptr<BVH> &world, std::ostream &writer, bool binary = false) {
+    std::string Render(const std::shared_ptr<BVH> &world, std::ostream &writer, bool binary = false, bool png = false) {
         // flatten: materials / textures de-duplicated by pointer, spheres in insertion order
         std::vector<rt_sphere> spheres;
         std::vector<rt_quad> quads;
@@ -282,6 +341,10 @@ struct Camera {
         std::string err = rc == RT_OK ? "" : rt_last_error();
         rt_scene_destroy(scene);
         if (!err.empty()) return err;
+        if (png) {
+            write_png(writer, rgb.data(), w, h);
+            return writer ? "" : "write failed";
+        }
         if (binary) {
             writer << "P6\n" << w << " " << h << "\n255\n";
             writer.write(reinterpret_cast<const char *>(rgb.data()), (std::streamsize)rgb.size());

@@ -127,3 +127,35 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29871")
     out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_png_writers_round_trip(tmp_path):
+    """The PNG output of the host mirrors (the reference's TODO at camera.go:196): api.encode_png and
+    rtgo::write_png (stored deflate blocks, no compression library) decode to the RGB8 they were given —
+    checked with Pillow, including an image larger than one 64 KiB deflate block."""
+    from PIL import Image
+    from raytracer_go_b200 import api
+    rng = np.random.default_rng(8)
+    for w, h in ((1, 1), (7, 5), (300, 200)):
+        rgb = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        path = tmp_path / f"py_{w}x{h}.png"
+        path.write_bytes(api.encode_png(rgb))
+        assert np.array_equal(np.asarray(Image.open(path).convert("RGB")), rgb)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "png_test.cpp"
+    src.write_text('#include <fstream>\n#include "%s/raytracer_go_b200/host/rtgo.hpp"\n'
+                   'int main(int argc, char **argv) {\n'
+                   '    const int w = atoi(argv[1]), h = atoi(argv[2]);\n'
+                   '    std::vector<uint8_t> rgb((size_t)w * h * 3);\n'
+                   '    for (size_t i = 0; i < rgb.size(); i++) rgb[i] = (uint8_t)((i * 2654435761u) >> 13);\n'
+                   '    std::ofstream f(argv[3], std::ios::binary);\n'
+                   '    rtgo::write_png(f, rgb.data(), w, h);\n'
+                   '    return 0;\n}\n' % root)
+    exe = tmp_path / "png_test"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), str(src)])
+    for w, h in ((1, 1), (13, 3), (400, 225)):
+        out = tmp_path / f"cpp_{w}x{h}.png"
+        subprocess.check_call([str(exe), str(w), str(h), str(out)])
+        i = np.arange(w * h * 3, dtype=np.uint64)
+        want = (((i * 2654435761) & 0xFFFFFFFF) >> 13).astype(np.uint8).reshape(h, w, 3)
+        assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), want)

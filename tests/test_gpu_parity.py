@@ -428,7 +428,8 @@ def test_render_multi_tile_split_is_bitwise_the_single_gpu_image(gpu, random_sce
 
 
 def test_binary_ppm_equals_text_ppm(gpu):
-    """RenderP6 (binary PPM, the reference's TODO at camera.go:196) carries the pixels of Render's P3."""
+    """RenderP6 / RenderPNG (binary PPM and PNG, the reference's TODO at camera.go:196) carry the pixels of
+    Render's P3."""
     import io
     world = _splitmix_scene()
     cam = api.NewCamera(16.0 / 9.0, 96, api.WithSamplesPerPixel(2), api.WithLookFrom(api.NewVec3(13, 2, 3)),
@@ -440,6 +441,11 @@ def test_binary_ppm_equals_text_ppm(gpu):
     raw = b.getvalue()
     assert raw.startswith(b"P6\n96 54\n255\n")
     assert np.array_equal(np.frombuffer(raw[len(b"P6\n96 54\n255\n"):], np.uint8), text)
+    from PIL import Image
+    png = io.BytesIO()
+    cam.RenderPNG(api.NewBVHFromWorld(world), png)
+    png.seek(0)
+    assert np.array_equal(np.asarray(Image.open(png).convert("RGB")).reshape(-1), text)
 
 
 def test_negative_and_zero_radius_spheres(gpu, orc):
