@@ -105,3 +105,31 @@ def test_c4_million_spheres(gpu, orc):
         rgb, acc, st = sc.render(cam, SEED, want_accum=True)
     assert st.samples == n_pix and st.rays > st.samples and np.isfinite(acc).all()
     assert rgb.std() > 5  # an actual picture, not a constant
+
+
+def test_c2_full_size_500spp_properties(gpu, orc, random_scene):
+    """Config C2 at its full size (1200x675, 500 spp, depth 50 = 405 M samples), through properties that do
+    not need a 405 M-sample oracle run: the sample count, determinism, additivity over sample ranges (the
+    500-sample sum equals the sum of two 250-sample renders up to FP32 association), the path statistics of
+    the oracle (segments per sample, hit fraction) and agreement of the mean image with the 2-spp frame the
+    oracle reproduces bit for bit (test_c2_full_size_equals_oracle)."""
+    cam = api.camera_from_options(scenes.camera_options(1200, 500))
+    n = 1200 * 675 * 500
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+        rgb2, acc2, _ = sc.render(cam, SEED, want_accum=True)
+        _, a0, s0 = sc.render(cam, SEED, 0, 250, want_accum=True)
+        _, a1, s1 = sc.render(cam, SEED, 250, 250, want_accum=True)
+    assert st.samples == n and s0.samples + s1.samples == n
+    assert np.array_equal(acc.view(np.uint32), acc2.view(np.uint32)) and np.array_equal(rgb, rgb2)
+    assert st.rays == s0.rays + s1.rays and st.hits == s0.hits + s1.hits     # the same 405 M paths
+    # FP32 sums of 500 terms added one by one (camera.go:256-260) against two sums of 250: each of the 250 later
+    # additions rounds at the ulp of a running sum twice as large (3e-5 near 350), hence a few 1e-5 relative
+    assert np.allclose(a0 + a1, acc, rtol=5e-5, atol=1e-4)
+    # the oracle's statistics on a 64x36 frame of the same camera: same scene, same path distribution
+    small = orc.camera_from_options(scenes.camera_options(64, 64))
+    _, _, rst = orc.render(random_scene, small, 99, order=orc.ORDER_ITERATIVE)
+    assert abs(st.rays / st.samples - rst.rays / rst.samples) < 0.05
+    assert abs(st.hits / st.rays - rst.hits / rst.rays) < 0.01
+    # a converged frame: every pixel within the noise of its own 2-spp estimate is not testable, the mean is
+    assert 0.2 < float(np.clip(acc / 500, 0, 1).mean()) < 0.8 and rgb.std() > 20
