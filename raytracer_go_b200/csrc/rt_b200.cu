@@ -561,8 +561,8 @@ static int launch_render_t(rt_scene *s, const RenderParams &p) {
     return RT_OK;
 }
 
-// (block, min blocks/SM) instances: 256x3 = 24 warps at <= 85 registers (default), 256x4 / 512x2 =
-// 32 warps at <= 64 registers.  RT_B200_BLOCK / RT_B200_MINB pick one (tuning knob).
+// (block, min blocks/SM) instances: 512x2 = 32 warps at <= 64 registers (default), 256x4 the same, 256x3 =
+// 24 warps at <= 85 registers.  RT_B200_BLOCK / RT_B200_MINB pick one (tuning knob).
 template <bool SMEM, bool COUNT, bool QUADS>
 static int launch_render_b(rt_scene *s, const RenderParams &p) {
     const int key = s->block * 10 + s->minb;
@@ -579,7 +579,7 @@ template <bool SMEM, bool COUNT, bool QUADS>
 static int launch_split(rt_scene *s, const RenderParams &p0) {
     RenderParams p = p0;
     CU(cudaMemsetAsync(s->d_queue_count, 0, RT_MAX_STAGES * sizeof(unsigned int), s->stream));
-    const size_t cap = (size_t)p.total_paths; // entries per array; layout: [buffer][o|d|t][cap]
+    // queue layout: [buffer][o | d | t][queue_stride entries]; the two buffers are used in turn
     float4 *buf[2] = {p.queue_o, p.queue_o + 3 * p.queue_stride};
     for (int k = 0; k < s->n_stages; k++) {
         float4 *out = buf[k & 1];
@@ -598,7 +598,6 @@ static int launch_split(rt_scene *s, const RenderParams &p0) {
                         : launch_primary_t<256, SMEM, COUNT, QUADS, false>(s, p);
         if (rc != RT_OK) return rc;
     }
-    (void)cap;
     p.stage_depth = s->n_stages; // the megakernel resumes the survivors of the last stage
     if (s->block == 512) return launch_render_t<512, 2, SMEM, COUNT, QUADS, true>(s, p);
     return launch_render_t<256, 3, SMEM, COUNT, QUADS, true>(s, p);
