@@ -463,3 +463,17 @@ def test_negative_and_zero_radius_spheres(gpu, orc):
     rrgb, racc, rst = orc.render(s, cam, SEED, order=orc.ORDER_ITERATIVE)
     assert (acc.view(np.uint32) == racc.view(np.uint32)).all(-1).mean() > 0.9995
     assert (rgb != rrgb).any(-1).mean() < 1e-3 and abs(int(st.rays) - int(rst.rays)) <= 1e-4 * rst.rays
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_ids(gpu, orc, seed):
+    """The traversal fuzz of tests/test_hostsim.py on the CUDA path: object IDs and hit t bit-exact on scenes
+    with radii over four decades, coincident / nested centres and negative radii."""
+    from tests.fuzz_scenes import fuzz_scene_and_rays
+    s, o, d, _ = fuzz_scene_and_rays(seed)
+    with api.Scene(s) as sc:
+        ids, ts = sc.trace(o, d)
+    rids, rts = orc.trace(s, o, d)
+    assert np.array_equal(ids, rids), int((ids != rids).sum())
+    hit = rids >= 0
+    assert np.array_equal(ts[hit].view(np.uint32), rts[hit].view(np.uint32))

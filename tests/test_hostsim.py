@@ -313,3 +313,17 @@ def test_fused_range_mappings_are_exact():
     ref = np.float32(-0.5) + r
     fused = (k.astype(np.float64) * 2.0 ** -24 - 0.5).astype(np.float32)
     assert np.array_equal(ref.view(np.uint32), fused.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_traversal_equals_world_hit(hs, orc, seed):
+    """Fuzz of the builder + flattened traversal against World.Hit on scenes the generators never make
+    (tests/fuzz_scenes.py), every leaf size."""
+    from tests.fuzz_scenes import fuzz_scene_and_rays
+    s, o, d, radius = fuzz_scene_and_rays(seed)
+    rids, rts = orc.trace(s, o, d)
+    for max_leaf in (1, 4, 8):
+        ids, ts, _, _ = hs_trace(hs, s, o, d, max_leaf=max_leaf, radius=radius)
+        assert np.array_equal(ids, rids), (seed, max_leaf, int((ids != rids).sum()))
+        hit = rids >= 0
+        assert np.array_equal(ts[hit].view(np.uint32), rts[hit].view(np.uint32))
