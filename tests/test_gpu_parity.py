@@ -477,3 +477,18 @@ def test_random_scenes_ids(gpu, orc, seed):
     assert np.array_equal(ids, rids), int((ids != rids).sum())
     hit = rids >= 0
     assert np.array_equal(ts[hit].view(np.uint32), rts[hit].view(np.uint32))
+
+
+@pytest.mark.parametrize("width,spp,depth", [(1, 1, 50), (3, 5, 50), (17, 2, 0), (33, 3, 1), (50, 1, 2), (129, 7, 50)])
+def test_ragged_sizes_match_oracle(gpu, orc, random_scene, width, spp, depth):
+    """Image sizes that are not a multiple of anything (1x1 included: imageHeight is clamped to 1,
+    camera.go:138-141), one sample, and the depth limits 0 / 1 / 2 (ray.go:33-35): bit-identical to the oracle."""
+    cam = _cam(width, spp, max_depth=depth)
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    rrgb, racc, rst = orc.render(random_scene, cam, SEED, order=orc.ORDER_ITERATIVE)
+    assert rgb.shape == rrgb.shape and st.samples == rst.samples == cam.width * cam.height * spp
+    assert np.array_equal(acc.view(np.uint32), racc.view(np.uint32))
+    assert np.array_equal(rgb, rrgb)
+    if depth == 0:
+        assert not acc.any()   # every sample is black
