@@ -431,6 +431,49 @@ class Camera:
         return None
 
 
+def resolve_host(accum, total_spp):
+    """camera.go:261 + vec3.go:141-166 on float32 sums that are already on the host: scale by 1/spp, sqrt,
+    clamp to [0, 1], * 255.999, truncate — the resolve kernel's arithmetic (every step is one correctly rounded
+    float32 operation, so numpy gives the same bytes)."""
+    mean = np.asarray(accum, np.float32) * np.float32(1.0 / total_spp)
+    with np.errstate(invalid="ignore"):
+        g = np.sqrt(mean)
+        g = np.where(g < 0, np.float32(0), np.where(g > 1, np.float32(1), g)).astype(np.float32)
+        g = g * np.float32(255.999)
+    return np.where(np.isnan(g), 0, g).astype(np.int32).astype(np.uint8)
+
+
+def render_checkpointed(data, cam, path, seed=scenes.RENDER_SEED, chunk_spp=64, device=0, stop_after=None):
+    """Resumable render (the reference has no checkpointing; SURVEY section 5 lists it as optional).  The
+    cam.spp samples of every pixel are rendered in chunks of `chunk_spp` global sample indices; after each chunk
+    the running FP32 sums and the sample cursor are written to `path` (.npz, replaced atomically).  A call that
+    finds a checkpoint of the same frame continues at its cursor, so an interrupted render followed by a
+    resumed one adds the same chunk sums in the same order as an uninterrupted one: bit-identical images.
+    `stop_after` = number of chunks to render in this call (to interrupt deliberately).
+    Returns (rgb or None while unfinished, sums, samples done)."""
+    import os
+    shape = (cam.height, cam.width, 3)
+    done, acc = 0, np.zeros(shape, np.float32)
+    if os.path.exists(path):
+        with np.load(path) as z:
+            if (tuple(z["shape"]) == shape and int(z["seed"]) == seed and int(z["spp"]) == cam.spp
+                    and int(z["chunk_spp"]) == chunk_spp and bytes(z["camera"].tobytes()) == bytes(cam)):
+                done, acc = int(z["done"]), z["acc"].astype(np.float32)
+    chunks = 0
+    with Scene(data, device) as sc:
+        while done < cam.spp and (stop_after is None or chunks < stop_after):
+            n = min(chunk_spp, cam.spp - done)
+            _, part, _ = sc.render(cam, seed, done, n, want_accum=True)
+            acc = acc + part
+            done += n
+            chunks += 1
+            tmp = path + ".tmp.npz"
+            np.savez(tmp, acc=acc, done=done, shape=np.array(shape), seed=seed, spp=cam.spp, chunk_spp=chunk_spp,
+                     camera=np.frombuffer(bytes(cam), np.uint8))
+            os.replace(tmp, path)
+    return (resolve_host(acc, cam.spp) if done >= cam.spp else None), acc, done
+
+
 def encode_png(rgb):
     """RGB8 (h, w, 3) -> PNG bytes: 8-bit truecolour, filter 0 on every scanline, one zlib stream."""
     import struct

@@ -492,3 +492,24 @@ def test_ragged_sizes_match_oracle(gpu, orc, random_scene, width, spp, depth):
     assert np.array_equal(rgb, rrgb)
     if depth == 0:
         assert not acc.any()   # every sample is black
+
+
+def test_checkpointed_render_resumes_bit_identically(gpu, random_scene, tmp_path):
+    """api.render_checkpointed: a render interrupted after 2 of 5 chunks and resumed from its checkpoint gives
+    the bytes of the uninterrupted chunked render; resolve_host is the resolve kernel's arithmetic."""
+    cam = _cam(160, 37)
+    full, acc_full, done = api.render_checkpointed(random_scene, cam, str(tmp_path / "a.npz"), SEED, chunk_spp=8)
+    assert done == 37 and full is not None
+    part, _, done = api.render_checkpointed(random_scene, cam, str(tmp_path / "b.npz"), SEED, chunk_spp=8, stop_after=2)
+    assert part is None and done == 16
+    res, acc_res, done = api.render_checkpointed(random_scene, cam, str(tmp_path / "b.npz"), SEED, chunk_spp=8)
+    assert done == 37
+    assert np.array_equal(acc_res.view(np.uint32), acc_full.view(np.uint32)) and np.array_equal(res, full)
+    # a finished checkpoint is returned as is; a different frame starts over
+    again, _, _ = api.render_checkpointed(random_scene, cam, str(tmp_path / "b.npz"), SEED, chunk_spp=8)
+    assert np.array_equal(again, full)
+    with api.Scene(random_scene) as sc:
+        rgb, acc, _ = sc.render(cam, SEED, want_accum=True)
+    assert np.array_equal(api.resolve_host(acc, cam.spp), rgb)                 # same arithmetic as the kernel
+    assert np.allclose(acc_full, acc, rtol=2e-5, atol=1e-5)                    # chunk sums vs one running sum
+    assert (np.abs(full.astype(int) - rgb.astype(int)) <= 1).all()

@@ -332,3 +332,18 @@ def test_perlin_noise_kat(orc):
     # a different table seed gives a different field
     s2 = scenes.perlin_demo_scene(seed=99)
     assert orc.texture(s2, 0, 0, 0, (0.3, 0.4, 0.5))[0] != orc.texture(s, 0, 0, 0, (0.3, 0.4, 0.5))[0]
+
+
+def test_host_resolve_equals_oracle_resolve(orc):
+    """api.resolve_host (numpy; used by the checkpointed render of the Python mirror) against the oracle's
+    restatement of camera.go:261 + vec3.go:141-166 on sums that cover negatives, values above 1, huge values,
+    zeros, NaN and the pixel-encode KATs of SURVEY section 4."""
+    from raytracer_go_b200 import api
+    rng = np.random.default_rng(12)
+    spp = 37
+    acc = (rng.uniform(-0.2, 1.4, size=(64, 97, 3)) * spp).astype(np.float32)
+    acc[0, 0] = (0.25 * spp, 1.0 * spp, 0.0)
+    acc[0, 1] = (0.7 * spp, 0.8 * spp, 1.0 * spp)
+    acc[0, 2] = (np.nan, np.inf, -np.inf)
+    acc[0, 3] = (1e30, 1e-30, -0.0)
+    assert np.array_equal(api.resolve_host(acc, spp), orc.resolve(acc, spp))
