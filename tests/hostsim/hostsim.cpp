@@ -3,8 +3,10 @@
 // checked against the oracle in this GPU-less container before GPU minutes are spent.
 // It is NOT a CPU path of the product: librt_b200.so never contains or loads this code, and only
 // `-m "not gpu"` tests build and call it.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../../include/rt_b200.h"
@@ -351,5 +353,95 @@ extern "C" int64_t hs_traversal_events_rays(const rt_scene_desc *d, const rt_cam
     }
 out:
     *n_rays_out = rays;
+    return n;
+}
+
+// Design exploration ("per-pixel beam"): for warps of 32 consecutive samples of one
+// pixel, walk the flat BVH once with the interval slab test that is exact for {origin box} x {direction box}
+// and report, per warp: node pairs visited, spheres in the visited leaves (the candidate list), how many of
+// them the rays would test if the list were sorted by beam entry distance and abandoned once every ray's
+// closest hit lies in front of the next candidate, and (for comparison) the per-ray traversal's node pairs
+// and sphere tests averaged over the 32 rays.  out = 5 floats per warp.
+extern "C" int64_t hs_beam_stats(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int64_t pixel_begin,
+                                 int64_t n_pixels, int64_t pixel_stride, int max_leaf, float *out) {
+    HostScene s;
+    load(d, max_leaf, 0, &s);
+    DevCamera c = make_dev_camera(*cam);
+    const F4 *nodes = s.bvh.nodes.data(); // (min.xyz, ref)(max.xyz, 0): the builder's padded boxes
+    int64_t n = 0;
+    for (int64_t pp = 0; pp < n_pixels; pp++) {
+        const int64_t pix = pixel_begin + pp * pixel_stride;
+        V3 o[32], dir[32];
+        float omin[3] = {INFINITY, INFINITY, INFINITY}, omax[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float dmin[3] = {INFINITY, INFINITY, INFINITY}, dmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float tbest[32];
+        double ray_pairs = 0, ray_sph = 0;
+        for (int k = 0; k < 32; k++) {
+            PathRng rng;
+            rng.init(seed, (uint32_t)pix, (uint32_t)k);
+            generate_ray(c, rng, (int)(pix % cam->width), (int)(pix / cam->width), o[k], dir[k]);
+            const float ov[3] = {o[k].x, o[k].y, o[k].z}, dv[3] = {dir[k].x, dir[k].y, dir[k].z};
+            for (int a = 0; a < 3; a++) {
+                omin[a] = std::min(omin[a], ov[a]), omax[a] = std::max(omax[a], ov[a]);
+                dmin[a] = std::min(dmin[a], dv[a]), dmax[a] = std::max(dmax[a], dv[a]);
+            }
+            LocalStack<64> stack;
+            HitRec h;
+            WorkCounters wc{0, 0};
+            trace_closest<LocalStack<64>, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
+                                                o[k], dir[k], 0.001f, INFINITY, stack, h, &wc);
+            tbest[k] = h.slot == RT_REF_NONE ? INFINITY : h.t;
+            ray_pairs += (double)wc.box_tests / 2, ray_sph += (double)wc.sphere_tests;
+        }
+        // entry distance of the beam into a box, or a negative value when it cannot touch it
+        auto beam_enter = [&](const F4 &lo, const F4 &hi) -> float {
+            const float l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+            float t0 = 0.001f, t1 = INFINITY;
+            for (int a = 0; a < 3; a++) {
+                const float A = h[a] - omin[a], B = l[a] - omax[a]; // omin + t dmin <= hi ; omax + t dmax >= lo
+                if (dmin[a] > 0) t1 = std::min(t1, A / dmin[a]);
+                else if (dmin[a] < 0) t0 = std::max(t0, A / dmin[a]);
+                else if (A < 0) return -1.0f;
+                if (dmax[a] > 0) t0 = std::max(t0, B / dmax[a]);
+                else if (dmax[a] < 0) t1 = std::min(t1, B / dmax[a]);
+                else if (B > 0) return -1.0f;
+            }
+            return t0 <= t1 ? t0 : -1.0f;
+        };
+        std::vector<uint32_t> stack;
+        std::vector<std::pair<float, uint32_t>> cand; // (beam entry distance of the leaf, sphere slot)
+        int pairs = 0;
+        auto visit_ref = [&](uint32_t ref, float t_enter) {
+            if (ref & RT_LEAF) {
+                if (ref == RT_REF_NONE || (ref & RT_LEAF_QUAD)) return;
+                const uint32_t first = (ref & RT_LEAF_SLOT_MASK) >> 3, count = (ref & 7u) + 1;
+                for (uint32_t q = first; q < first + count; q++) cand.push_back({t_enter, q});
+            } else {
+                stack.push_back(ref);
+            }
+        };
+        visit_ref(s.bvh.root_ref, 0.0f);
+        while (!stack.empty()) {
+            const uint32_t ref = stack.back();
+            stack.pop_back();
+            pairs++;
+            for (int ch = 0; ch < 2; ch++) {
+                const F4 &lo = nodes[2 * (ref + ch)], &hi = nodes[2 * (ref + ch) + 1];
+                const float t = beam_enter(lo, hi);
+                if (t >= 0) visit_ref(as_uint(lo.w), t);
+            }
+        }
+        std::sort(cand.begin(), cand.end());
+        float worst = 0; // the farthest closest-hit among the 32 rays (infinite if one of them misses)
+        for (int k = 0; k < 32; k++) worst = std::max(worst, tbest[k]);
+        int tested = 0;
+        for (auto &cd : cand) {
+            if (cd.first > worst) break;
+            tested++;
+        }
+        out[5 * n] = (float)pairs, out[5 * n + 1] = (float)cand.size(), out[5 * n + 2] = (float)tested;
+        out[5 * n + 3] = (float)(ray_pairs / 32), out[5 * n + 4] = (float)(ray_sph / 32);
+        n++;
+    }
     return n;
 }
