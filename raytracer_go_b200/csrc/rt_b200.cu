@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -527,12 +528,30 @@ static double dist_to_center(const rt_scene *s, const float *p) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair, not to a scene
+// handle: with two live scenes of different size, setting it per handle would let the smaller scene
+// lower the limit under the larger one (cudaErrorInvalidValue at its next launch).  It is therefore
+// kept as a per-device, per-kernel high-water mark that is only ever raised.
+template <class K>
+static int ensure_dyn_smem(K kern, int device, size_t smem) {
+    if (smem <= 48 * 1024) return RT_OK;
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> high;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &h = high[std::make_pair((const void *)kern, device)];
+    if (smem > h) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h = smem;
+    }
+    return RT_OK;
+}
+
 template <int BLOCK, bool SMEM, bool COUNT, bool QUADS, bool FIRST>
 static int launch_primary_t(rt_scene *s, const RenderParams &p) {
     auto kern = primary_stage_kernel<BLOCK, SMEM, COUNT, QUADS, FIRST>;
     if (s->primary_grid[COUNT][FIRST] == 0) {
         const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RC(ensure_dyn_smem(kern, s->device, smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
         if (per_sm < 1) return fail(RT_ERR_CUDA, "primary stage does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
@@ -549,7 +568,7 @@ static int launch_render_t(rt_scene *s, const RenderParams &p) {
     auto kern = render_kernel<BLOCK, MINB, SMEM, COUNT, QUADS, SPLIT>;
     if (s->grid_cache[COUNT] == 0) { // once per handle: opt in to the dynamic shared memory, size the grid
         const size_t smem = SMEM ? smem_total_bytes(p.sc, BLOCK) : 0;
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RC(ensure_dyn_smem(kern, s->device, smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
         if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM (block %d, smem %zu)", BLOCK, smem);
@@ -1074,7 +1093,7 @@ static int launch_trace_t(rt_scene *s, const float *d_o, const float *d_d, int64
     const size_t smem = smem_total_bytes(s->dev, BLOCK);
     if (s->use_smem && smem <= s->smem_optin) {
         auto kern = trace_kernel<BLOCK, true, QUADS>;
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RC(ensure_dyn_smem(kern, s->device, smem));
         kern<<<std::min(grid, s->sm_count * 2), BLOCK, smem, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);
     } else {
         trace_kernel<BLOCK, false, QUADS><<<grid, BLOCK, 0, s->stream>>>(s->dev, d_o, d_d, n, tmin, tmax, d_id, d_t);

@@ -513,3 +513,26 @@ def test_checkpointed_render_resumes_bit_identically(gpu, random_scene, tmp_path
     assert np.array_equal(api.resolve_host(acc, cam.spp), rgb)                 # same arithmetic as the kernel
     assert np.allclose(acc_full, acc, rtol=2e-5, atol=1e-5)                    # chunk sums vs one running sum
     assert (np.abs(full.astype(int) - rgb.astype(int)) <= 1).all()
+
+
+def test_two_live_scenes_of_different_size_render_alternately(gpu, orc, random_scene):
+    """Two handles on one device whose shared-memory stagings differ (both above 48 KB would be the failing case
+    of a per-handle cudaFuncSetAttribute; the attribute is a per-device high-water mark): renders alternate
+    between them and each stays bit-identical to its own first render."""
+    big = random_scene                                             # ~485 spheres: ~79 KB of dynamic shared memory
+    sp = random_scene.spheres[:300].copy()                         # a smaller staging of the same kernels
+    small = scenes.SceneData(sp, random_scene.materials, random_scene.textures, name="random300")
+    cam = _cam(160, 6)
+    with api.Scene(big) as a, api.Scene(small) as b:
+        ra0, acc_a0, _ = a.render(cam, SEED, want_accum=True)
+        rb0, acc_b0, _ = b.render(cam, SEED, want_accum=True)
+        for _ in range(2):
+            ra, acc_a, _ = a.render(cam, SEED, want_accum=True)
+            rb, acc_b, _ = b.render(cam, SEED, want_accum=True)
+            assert np.array_equal(acc_a.view(np.uint32), acc_a0.view(np.uint32)) and np.array_equal(ra, ra0)
+            assert np.array_equal(acc_b.view(np.uint32), acc_b0.view(np.uint32)) and np.array_equal(rb, rb0)
+        n = cam.width * cam.height
+        ro, rd = orc.primary_rays(cam, SEED, 0, n, 0, 1)
+        ids_a, _ = a.trace(ro, rd)
+        ids_b, _ = b.trace(ro, rd)
+    assert np.array_equal(ids_a, orc.trace(big, ro, rd)[0]) and np.array_equal(ids_b, orc.trace(small, ro, rd)[0])
