@@ -543,9 +543,69 @@ static void make_device_nodes(FlatBvh *bvh) {
         bvh->dev_nodes[i] = a, bvh->dev_nodes[i + 1] = b;
     }
     });
+    // walk pairs of the leaf-start chains: copies of two real nodes side by side (see bvh_build.h)
+    const size_t n_real = bvh->nodes.size(), n_walk = bvh->walk_src.size() / 2;
+    bvh->dev_nodes.resize(n_real + 4 * n_walk);
+    for (size_t k = 0; k < n_walk; k++) {
+        F4 *dst = &bvh->dev_nodes[n_real + 4 * k];
+        const uint32_t s0 = bvh->walk_src[2 * k], s1 = bvh->walk_src[2 * k + 1];
+        dst[0] = bvh->dev_nodes[2 * (size_t)s0], dst[1] = bvh->dev_nodes[2 * (size_t)s0 + 1];
+        if (s1 != RT_REF_NONE) {
+            dst[2] = bvh->dev_nodes[2 * (size_t)s1], dst[3] = bvh->dev_nodes[2 * (size_t)s1 + 1];
+        } else {
+            // no second sibling: a box that cannot be hit (far plane in front of the near plane on every axis);
+            // should the slab test ever degenerate (zero reciprocal), its ref repeats the first box's, which is harmless
+            dst[2] = dst[0], dst[3] = dst[1];
+            dst[2].x = dst[2].y = dst[2].z = 0.0f;
+            dst[3].x = dst[3].y = dst[3].z = -1e30f;
+        }
+    }
 }
 
-void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out, const double *center) {
+// Leaf-start chains (bvh_build.h).  Serial; called for scenes small enough to be staged in shared memory.
+static void build_leaf_start(FlatBvh *bvh) {
+    const size_t n_nodes = bvh->nodes.size() / 2;
+    bvh->walk_src.clear(), bvh->chains.clear();
+    bvh->sph_chain.assign(bvh->sph.size(), RT_REF_NONE);
+    bvh->quad_chain.assign(bvh->quad_prim.size(), RT_REF_NONE);
+    if (n_nodes == 0) return;
+    auto ref_of = [&](size_t i) {
+        uint32_t r;
+        memcpy(&r, &bvh->nodes[2 * i].w, 4);
+        return r;
+    };
+    std::vector<uint32_t> parent(n_nodes / 2, RT_REF_NONE); // per pair: the node whose ref it is
+    for (size_t i = 0; i < n_nodes; i++)
+        if (!(ref_of(i) & RT_LEAF)) parent[ref_of(i) / 2] = (uint32_t)i;
+    std::vector<uint32_t> pair_of(n_nodes, RT_REF_NONE); // walk pair whose first box is the sibling of node i
+    std::vector<uint32_t> chain;
+    for (size_t leaf = 0; leaf < n_nodes; leaf++) {
+        const uint32_t lref = ref_of(leaf);
+        if (!(lref & RT_LEAF)) continue;
+        chain.clear();
+        for (uint32_t n = (uint32_t)leaf;;) {
+            const uint32_t up = parent[n / 2]; // parent of n (RT_REF_NONE: n is a child of the root)
+            if (pair_of[n] == RT_REF_NONE) {
+                pair_of[n] = (uint32_t)(n_nodes + bvh->walk_src.size()); // 2 device nodes per walk pair, appended after the real ones
+                bvh->walk_src.push_back(n ^ 1u);
+                bvh->walk_src.push_back(up == RT_REF_NONE ? RT_REF_NONE : (up ^ 1u));
+            }
+            chain.push_back(pair_of[n]);
+            if (up == RT_REF_NONE) break;
+            n = parent[up / 2];
+            if (n == RT_REF_NONE) break;
+        }
+        const uint32_t off = (uint32_t)bvh->chains.size();
+        bvh->chains.push_back((uint32_t)chain.size());
+        for (size_t k = chain.size(); k-- > 0;) bvh->chains.push_back(chain[k]); // root side first: the deepest pair is popped first
+        bvh->chains.push_back(lref);
+        const uint32_t first = (lref & RT_LEAF_SLOT_MASK) >> 3, count = (lref & 7u) + 1;
+        for (uint32_t q = first; q < first + count; q++) ((lref & RT_LEAF_QUAD) ? bvh->quad_chain : bvh->sph_chain)[q] = off;
+    }
+}
+
+void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out, const double *center,
+                    bool leaf_start) {
     *out = FlatBvh();
     const size_t n = prims.size();
     if (n == 0) return;
@@ -606,6 +666,7 @@ void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, 
     lap("resize");
     out->root_ref = b.emit(root, 0, 0, 0);
     lap("emit");
+    if (leaf_start) build_leaf_start(out), lap("leaf start");
     make_device_nodes(out);
     lap("device nodes");
 }

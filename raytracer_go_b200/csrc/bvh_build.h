@@ -42,7 +42,16 @@ using RawVec = std::vector<T, NoInitAlloc<T>>;
 struct FlatBvh {
     RawVec<F4> nodes;          // 2 x F4 per node (min.xyz, ref)(max.xyz, 0), siblings adjacent, depth-first order
     RawVec<F4> dev_nodes;      // the same nodes as the kernels read them: (centre.xyz, ref)(half-extent.xyz, 0),
-                               // [c - h, c + h] encloses [min, max] (box_test in rt_trace.h)
+                               // [c - h, c + h] encloses [min, max] (box_test in rt_trace.h); followed by the
+                               // "walk pairs" of the leaf-start chains (below) when those were built
+    // Leaf start (build_leaf_start): a ray that leaves a known primitive starts inside its leaf's box and inside
+    // the boxes of all the leaf's ancestors, so those need no test — only the siblings along the path do.  Two
+    // siblings are copied side by side into a "walk pair" (a pair of device nodes like any other) and the refs of a
+    // leaf's walk pairs form its chain; the kernel pushes the chain, starts at the leaf and traverses as usual.
+    RawVec<uint32_t> walk_src;   // 2 per walk pair: the real nodes copied into it (second = RT_REF_NONE: a never-hit dummy)
+    RawVec<uint32_t> chains;     // per leaf: [len, len walk-pair refs (root side first), the leaf's own ref]
+    RawVec<uint32_t> sph_chain;  // per sphere slot: offset of its leaf's chain in `chains`
+    RawVec<uint32_t> quad_chain; // per quad slot: likewise
     RawVec<F4> sph;            // per sphere slot: centre, radius
     RawVec<I2> meta;           // per sphere slot: object ID, material index
     RawVec<uint32_t> sph_prim; // per sphere slot: index into ScenePrims.spheres
@@ -55,7 +64,8 @@ struct FlatBvh {
 
 // max_leaf in [1, RT_MAX_LEAF].  origin_radius: rt_scene_desc.ray_origin_radius (0 = derive).
 // `center` (optional): compute_scene_center's m, if the caller has it already.
-void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out, const double *center = nullptr);
+void build_flat_bvh(const ScenePrims &prims, float origin_radius, int max_leaf, FlatBvh *out, const double *center = nullptr,
+                    bool leaf_start = false);
 // Recompute all boxes for a (larger) origin radius; topology and slot order are unchanged.
 void refit_flat_bvh(const ScenePrims &prims, float origin_radius, FlatBvh *bvh);
 // Per-axis median m of the primitive centres, the 90th percentile of |c - m| + extent, and

@@ -177,6 +177,7 @@ struct rt_scene {
     size_t primary_smem[2][2] = {{0, 0}, {0, 0}};
     // device buffers
     F4 *d_nodes = nullptr, *d_sph = nullptr, *d_mats = nullptr, *d_quads = nullptr;
+    uint32_t *d_chains = nullptr; // leaf-start chains + per-slot chain offsets (one buffer)
     bool has_quads = false;
     I2 *d_meta = nullptr;
     DevImage *d_images = nullptr;
@@ -296,7 +297,7 @@ static void free_scene(rt_scene *s) {
     // every render call returns after its stream has drained, so nothing is still using these
     cudaStream_t st = s->own_stream;
     scene_free(s->d_nodes, st), scene_free(s->d_sph, st), scene_free(s->d_mats, st), scene_free(s->d_meta, st);
-    scene_free(s->d_images, st), scene_free(s->d_quads, st), scene_free(s->d_perlins, st);
+    scene_free(s->d_images, st), scene_free(s->d_quads, st), scene_free(s->d_perlins, st), scene_free(s->d_chains, st);
     for (auto p : s->d_texels) scene_free(p, st);
     scene_free(s->d_counter, st), scene_free(s->d_stats, st), scene_free(s->d_queue_count, st);
     for (auto e : s->events) cudaEventDestroy(e);
@@ -320,13 +321,19 @@ struct HostSceneParts {
     bool fixed_radius = false;
     FlatBvh bvh;
 };
+// Leaf-start chains (bvh_build.h) are built for scenes that can be staged in shared memory; RT_B200_LEAF_START=0
+// turns them off (tuning knob / A-B measurement), RT_B200_LEAF_START_MAX moves the size limit.
+static bool want_leaf_start(size_t n_prims) {
+    return env_int("RT_B200_LEAF_START", 1) != 0 && n_prims <= (size_t)env_int("RT_B200_LEAF_START_MAX", 16384);
+}
+
 static int host_scene_parts(const rt_scene_desc *desc, HostSceneParts *h) {
     if (!load_scene_prims(desc, &h->prims))
         return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
     compute_scene_center(h->prims, h->center, &h->extent90, &h->surface_extent);
     h->fixed_radius = desc->ray_origin_radius > 0;
     h->origin_radius = h->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * h->extent90);
-    build_flat_bvh(h->prims, h->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &h->bvh, h->center);
+    build_flat_bvh(h->prims, h->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &h->bvh, h->center, want_leaf_start(h->prims.size()));
     return RT_OK;
 }
 
@@ -363,7 +370,8 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
         s->fixed_radius = desc->ray_origin_radius > 0;
         s->origin_radius = s->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
         lap("scene centre");
-        build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh, s->center);
+        build_flat_bvh(s->prims, s->origin_radius, env_int("RT_B200_MAX_LEAF", 4), &s->bvh, s->center,
+                       want_leaf_start(s->prims.size()));
         lap("bvh build");
     }
 
@@ -371,7 +379,8 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
     pack_materials(desc, &mats);
     lap("materials");
 
-    const size_t n_nodes = s->bvh.nodes.size() / 2, n_slots = s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
+    // device nodes = the tree's nodes + the walk pairs of the leaf-start chains
+    const size_t n_nodes = s->bvh.dev_nodes.size() / 2, n_slots = s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
     RC(scene_alloc(&s->d_quads, std::max<size_t>(1, n_qslots) * 16 * RT_QUAD_F4, device, s->stream));
     if (n_qslots)
         CU(cudaMemcpyAsync(s->d_quads, s->bvh.quad.data(), n_qslots * 16 * RT_QUAD_F4, cudaMemcpyHostToDevice, s->stream));
@@ -388,6 +397,16 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
         CU(cudaMemcpyAsync(s->d_meta, s->bvh.meta.data(), n_slots * 8, cudaMemcpyHostToDevice, s->stream));
     }
     if (!mats.empty()) CU(cudaMemcpyAsync(s->d_mats, mats.data(), mats.size() * 16, cudaMemcpyHostToDevice, s->stream));
+    if (!s->bvh.chains.empty()) { // leaf start: chains, then the per-slot chain offsets of spheres and quads, in one buffer
+        const size_t nc = s->bvh.chains.size(), total = nc + n_slots + n_qslots;
+        RC(scene_alloc(&s->d_chains, total * 4, device, s->stream));
+        CU(cudaMemcpyAsync(s->d_chains, s->bvh.chains.data(), nc * 4, cudaMemcpyHostToDevice, s->stream));
+        if (n_slots) CU(cudaMemcpyAsync(s->d_chains + nc, s->bvh.sph_chain.data(), n_slots * 4, cudaMemcpyHostToDevice, s->stream));
+        if (n_qslots)
+            CU(cudaMemcpyAsync(s->d_chains + nc + n_slots, s->bvh.quad_chain.data(), n_qslots * 4, cudaMemcpyHostToDevice, s->stream));
+        s->dev.chains = s->d_chains, s->dev.sph_chain = s->d_chains + nc, s->dev.quad_chain = s->d_chains + nc + n_slots;
+        s->dev.n_chain_words = (uint32_t)nc;
+    }
 
     // images: RGB16 -> (r, g, b, 0) uint16x4 so a texel is one 8-byte load
     std::vector<DevImage> imgs(desc->n_images);
@@ -445,11 +464,15 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
     // registers): C2 +6 %, Cornell box +3 % (profiles/r01aj, r01ak); the kernels wait on fixed-latency
     // dependencies and shared-memory loads, so 8 more warps per SM buy more than 16 more registers.
     // 640 x 2 (40 warps, 48 registers, 200 B of spills) is 6.6 % slower again (profiles/r01al).
-    s->block = env_int("RT_B200_BLOCK", 512);
-    if (s->block != 256 && s->block != 512) s->block = 512;
-    s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : 2);
-    s->pblock = env_int("RT_B200_PBLOCK", 512); // block size of the primary stage (256 or 512)
-    if (s->pblock != 256 && s->pblock != 512) s->pblock = 512;
+    // 1024 x 1 keeps the 32 warps and stages the scene ONCE per SM instead of twice: twice the shared-memory budget
+    // (a scene + its leaf-start walk pairs that do not fit 2 x 113 KB fit 1 x 227 KB).  RT_B200_BLOCK = 0 (default):
+    // 512 x 2 when the staging fits it, else 1024 x 1.
+    const int want_block = env_int("RT_B200_BLOCK", 0);
+    s->block = want_block == 256 || want_block == 512 || want_block == 1024 ? want_block : 512;
+    s->minb = env_int("RT_B200_MINB", s->block == 256 ? 3 : s->block == 512 ? 2 : 1);
+    if (s->block == 1024) s->minb = 1;
+    const int want_pblock = env_int("RT_B200_PBLOCK", 0); // block size of the primary stage
+    s->pblock = want_pblock == 256 || want_pblock == 512 || want_pblock == 1024 ? want_pblock : (s->block == 1024 ? 1024 : 512);
     {
         const char *kv = getenv("RT_B200_KERNEL");
         // default: two-stage ("split"); RT_B200_KERNEL=mega selects the one-stage megakernel
@@ -461,9 +484,16 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
     // which costs ~2 % on C2 — less than running fewer warps would
     int smem_sm = 0;
     CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    const size_t budget = std::min<size_t>(s->smem_optin, (size_t)smem_sm / (size_t)std::max(1, s->minb) - 1024);
-    s->use_smem = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK &&
-                  smem_total_bytes(s->dev, s->block) <= budget;
+    auto fits = [&](int block, int minb) {
+        const size_t budget = std::min<size_t>(s->smem_optin, (size_t)smem_sm / (size_t)std::max(1, minb) - 1024);
+        return smem_total_bytes(s->dev, block) <= budget;
+    };
+    const bool smem_ok = env_int("RT_B200_NO_SMEM", 0) == 0 && s->dev.stack_depth <= RT_LOCAL_STACK;
+    s->use_smem = smem_ok && fits(s->block, s->minb) && fits(s->pblock, s->pblock == 1024 ? 1 : 2);
+    if (smem_ok && !s->use_smem && want_block == 0 && want_pblock == 0 && fits(1024, 1)) {
+        s->block = s->pblock = 1024, s->minb = 1;
+        s->use_smem = true;
+    }
     if (timing) CU(cudaStreamSynchronize(s->stream));
     lap("alloc + upload");
     return RT_OK;
@@ -580,13 +610,13 @@ static int launch_render_t(rt_scene *s, const RenderParams &p) {
     return RT_OK;
 }
 
-// (block, min blocks/SM) instances: 512x2 = 32 warps at <= 64 registers (default), 256x4 the same, 256x3 =
-// 24 warps at <= 85 registers.  RT_B200_BLOCK / RT_B200_MINB pick one (tuning knob).
+// (block, min blocks/SM) instances: 512x2 = 32 warps at <= 64 registers (default), 1024x1 the same with one
+// staging of the scene per SM, 256x3 = 24 warps at <= 85 registers.  RT_B200_BLOCK / RT_B200_MINB pick one (tuning knob).
 template <bool SMEM, bool COUNT, bool QUADS>
 static int launch_render_b(rt_scene *s, const RenderParams &p) {
     const int key = s->block * 10 + s->minb;
     switch (key) {
-    case 2564: return launch_render_t<256, 4, SMEM, COUNT, QUADS>(s, p);
+    case 10241: return launch_render_t<1024, 1, SMEM, COUNT, QUADS>(s, p);
     case 5122: return launch_render_t<512, 2, SMEM, COUNT, QUADS>(s, p);
     default: return launch_render_t<256, 3, SMEM, COUNT, QUADS>(s, p);
     }
@@ -609,7 +639,10 @@ static int launch_split(rt_scene *s, const RenderParams &p0) {
         p.in_count = k ? s->d_queue_count + k - 1 : nullptr;
         p.stage_depth = k;
         int rc;
-        if (s->pblock == 512)
+        if (s->pblock == 1024)
+            rc = k == 0 ? launch_primary_t<1024, SMEM, COUNT, QUADS, true>(s, p)
+                        : launch_primary_t<1024, SMEM, COUNT, QUADS, false>(s, p);
+        else if (s->pblock == 512)
             rc = k == 0 ? launch_primary_t<512, SMEM, COUNT, QUADS, true>(s, p)
                         : launch_primary_t<512, SMEM, COUNT, QUADS, false>(s, p);
         else
@@ -618,6 +651,7 @@ static int launch_split(rt_scene *s, const RenderParams &p0) {
         if (rc != RT_OK) return rc;
     }
     p.stage_depth = s->n_stages; // the megakernel resumes the survivors of the last stage
+    if (s->block == 1024) return launch_render_t<1024, 1, SMEM, COUNT, QUADS, true>(s, p);
     if (s->block == 512) return launch_render_t<512, 2, SMEM, COUNT, QUADS, true>(s, p);
     return launch_render_t<256, 3, SMEM, COUNT, QUADS, true>(s, p);
 }

@@ -31,13 +31,17 @@ struct DevScene {
     const F4 *mats;
     DevTex tex;      // images and Perlin tables (global memory)
     const F4 *quads; // RT_QUAD_F4 x F4 per quad slot
-    uint32_t root_ref, n_nodes, n_slots, n_mats, n_quad_slots;
+    // leaf start (rt_trace.h, bvh_build.h): chains == nullptr when the scene was built without it
+    const uint32_t *chains, *sph_chain, *quad_chain;
+    uint32_t n_chain_words;
+    uint32_t root_ref, n_nodes, n_slots, n_mats, n_quad_slots; // n_nodes counts the walk pairs too
     uint32_t stack_depth; // entries per thread for the shared-memory stack
 };
 
 static size_t scene_smem_bytes(const DevScene &s) {
     return (size_t)s.n_nodes * 32 + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 +
-           (size_t)s.n_quad_slots * 16 * RT_QUAD_F4 + (size_t)s.n_slots * 8;
+           (size_t)s.n_quad_slots * 16 * RT_QUAD_F4 + (size_t)s.n_slots * 8 +
+           (s.chains ? ((size_t)s.n_chain_words + s.n_slots + s.n_quad_slots) * 4 : 0);
 }
 
 #define RT_LOCAL_STACK 64
@@ -46,8 +50,15 @@ static size_t scene_smem_bytes(const DevScene &s) {
 struct SmemScene {
     const F4 *nodes, *sph, *mats, *quads;
     const I2 *meta;
+    const uint32_t *chains, *sph_chain, *quad_chain;
     uint32_t *stack;
 };
+
+// Chain of the leaf that holds hit slot `slot` (leaf start), RT_REF_NONE without chains.
+__device__ __forceinline__ uint32_t chain_of_slot(const uint32_t *sph_chain, const uint32_t *quad_chain, uint32_t slot) {
+    if (sph_chain == nullptr) return RT_REF_NONE;
+    return (slot & RT_HIT_QUAD) ? quad_chain[slot & ~RT_HIT_QUAD] : sph_chain[slot];
+}
 
 __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned char *smem) {
     F4 *nodes = reinterpret_cast<F4 *>(smem);
@@ -55,7 +66,15 @@ __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned ch
     F4 *mats = sph + sc.n_slots;
     F4 *quads = mats + 2 * (size_t)sc.n_mats;
     I2 *meta = reinterpret_cast<I2 *>(quads + (size_t)RT_QUAD_F4 * sc.n_quad_slots);
-    uint32_t *stack = reinterpret_cast<uint32_t *>(meta + sc.n_slots + (sc.n_slots & 1));
+    uint32_t *chains = reinterpret_cast<uint32_t *>(meta + sc.n_slots + (sc.n_slots & 1));
+    uint32_t *sph_chain = chains + (sc.chains ? sc.n_chain_words : 0);
+    uint32_t *quad_chain = sph_chain + (sc.chains ? sc.n_slots : 0);
+    uint32_t *stack = quad_chain + (sc.chains ? sc.n_quad_slots : 0);
+    if (sc.chains) {
+        for (uint32_t i = threadIdx.x; i < sc.n_chain_words; i += blockDim.x) chains[i] = __ldg(sc.chains + i);
+        for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) sph_chain[i] = __ldg(sc.sph_chain + i);
+        for (uint32_t i = threadIdx.x; i < sc.n_quad_slots; i += blockDim.x) quad_chain[i] = __ldg(sc.quad_chain + i);
+    }
     const uint4 *src;
     uint4 *dst;
     src = reinterpret_cast<const uint4 *>(sc.nodes), dst = reinterpret_cast<uint4 *>(nodes);
@@ -72,6 +91,7 @@ __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned ch
     __syncthreads();
     SmemScene r;
     r.nodes = nodes, r.sph = sph, r.mats = mats, r.quads = quads, r.meta = meta, r.stack = stack;
+    r.chains = sc.chains ? chains : nullptr, r.sph_chain = sc.chains ? sph_chain : nullptr, r.quad_chain = quad_chain;
     return r;
 }
 
@@ -102,8 +122,8 @@ struct RenderParams {
     // two-stage mode (primary_stage_kernel + render_kernel<SPLIT>): paths that survive their first
     // segment, as three float4 arrays of capacity total_paths
     float4 *queue_o;           // (o.xyz, bits path index)
-    float4 *queue_d;           // (d.xyz, bits next Philox block)
-    float4 *queue_t;           // (throughput.xyz, 0)
+    float4 *queue_d;           // (d.xyz, bits next Philox block | bit 31: radiance parked in the sample slot)
+    float4 *queue_t;           // (throughput.xyz, bits hit slot of the first segment: where the next ray starts)
     unsigned int *queue_count; // entries appended by the stage that fills queue_o/d/t
     // stage k > 0 of the staged mode reads the survivors of stage k-1 here (same layout)
     const float4 *in_o, *in_d, *in_t;
@@ -140,10 +160,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
     const I2 *meta = p.sc.meta;
+    const uint32_t *chains = p.sc.chains, *sph_chain = p.sc.chains ? p.sc.sph_chain : nullptr, *quad_chain = p.sc.quad_chain;
     uint32_t *stack_mem = nullptr;
     if (SMEM) {
         SmemScene s = stage_scene(p.sc, smem_raw);
         nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta, stack_mem = s.stack;
+        chains = s.chains, sph_chain = s.sph_chain, quad_chain = s.quad_chain;
     }
     typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
     Stack stack;
@@ -161,6 +183,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 
     bool alive = false;
     uint32_t idx = 0;
+    uint32_t start = RT_REF_NONE; // leaf-start chain of the primitive the current ray leaves (RT_REF_NONE: a camera ray)
     int depth = 0;
     V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1), rad = v3(0, 0, 0);
     PathRng rng;
@@ -193,10 +216,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                     idx = __float_as_uint(qo.w);
                     const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                     rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
-                    rng.block = __float_as_uint(qd.w);
+                    rng.block = __float_as_uint(qd.w) & 0x7fffffffu;
                     o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z);
                     thr = v3(qt.x, qt.y, qt.z), rad = v3(0, 0, 0), depth = p.stage_depth;
-                    if (qt.w != 0.0f) { // radiance emitted on the first segment (no reference material does this)
+                    start = chain_of_slot(sph_chain, quad_chain, __float_as_uint(qt.w));
+                    if (__float_as_uint(qd.w) & 0x80000000u) { // radiance emitted on the first segment (no reference material does this)
                         const float4 r0 = p.samples[idx];
                         rad = v3(r0.x, r0.y, r0.z);
                     }
@@ -208,6 +232,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                     rng.init(p.seed, pixel, p.sample_begin + k);
                     generate_ray(p.cam, rng, i, j, o, d);
                     thr = v3(1, 1, 1), rad = v3(0, 0, 0), depth = 0;
+                    start = RT_REF_NONE;
                 }
                 alive = true;
             }
@@ -218,7 +243,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 
         // ---- one path segment: ray.go:32-54 unrolled front to back ----
         HitRec h;
-        trace_closest<Stack, COUNT, QUADS, SMEM>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads);
+        trace_closest<Stack, COUNT, QUADS, SMEM>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+                                                 chains, start);
         n_rays++;
         bool done;
         if (h.slot == RT_REF_NONE) {
@@ -240,6 +266,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
                 scattered = shade_hit(m0, m1, p.sc.tex, s, h.t, rng, o, d, atten, emitted);
             }
             rad = rad + thr * emitted; // ray.go:41,50
+            start = chain_of_slot(sph_chain, quad_chain, h.slot); // the scattered ray leaves this primitive
             if (!scattered) {
                 done = true; // ray.go:44-46
             } else {
@@ -283,9 +310,11 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
     const I2 *meta = p.sc.meta;
     typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
     Stack stack;
+    const uint32_t *chains = p.sc.chains, *sph_chain = p.sc.chains ? p.sc.sph_chain : nullptr, *quad_chain = p.sc.quad_chain;
     if constexpr (SMEM) {
         SmemScene s = stage_scene(p.sc, smem_raw);
         nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta;
+        chains = s.chains, sph_chain = s.sph_chain, quad_chain = s.quad_chain;
         stack.base = s.stack + threadIdx.x;
         stack.stride = BLOCK;
     }
@@ -302,10 +331,11 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
         uint32_t idx = item;
         bool survive = false, carries = false;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1);
-        uint32_t block = 0;
+        uint32_t block = 0, hit_slot = RT_REF_NONE;
         if (item < n_items) {
             PathRng rng;
             V3 rad = v3(0, 0, 0);
+            uint32_t start = RT_REF_NONE;
             if (FIRST) {
                 const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                 const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
@@ -317,16 +347,19 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 idx = __float_as_uint(qo.w);
                 const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                 rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
-                rng.block = __float_as_uint(qd.w);
+                rng.block = __float_as_uint(qd.w) & 0x7fffffffu;
                 o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z), thr = v3(qt.x, qt.y, qt.z);
-                if (qt.w != 0.0f) { // radiance parked by an earlier stage
+                start = chain_of_slot(sph_chain, quad_chain, __float_as_uint(qt.w));
+                if (__float_as_uint(qd.w) & 0x80000000u) { // radiance parked by an earlier stage
                     const float4 r0 = p.samples[idx];
                     rad = v3(r0.x, r0.y, r0.z);
                 }
             }
             HitRec h;
-            trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads);
+            trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+                                               FIRST ? nullptr : chains, start);
             n_rays++;
+            hit_slot = h.slot;
             if (h.slot == RT_REF_NONE) {
                 rad = rad + thr * p.cam.background; // ray.go:53
             } else {
@@ -390,8 +423,8 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
         if (survive) {
             const uint32_t e = first_entry + __popc(m & ((1u << lane) - 1u));
             p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
-            p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block));
-            p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, carries ? 1.0f : 0.0f);
+            p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block | (carries ? 0x80000000u : 0u)));
+            p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(hit_slot)); // the primitive the survivor leaves
         }
     }
     unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};

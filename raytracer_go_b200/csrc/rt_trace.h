@@ -214,11 +214,20 @@ RT_HD int32_t slot_object_id(uint32_t slot, const I2 *__restrict__ meta, const F
 // of branches.  Pays for incoherent warps, whose lanes disagree nearly every step (secondary
 // megakernel, shared-memory stack: +1.4 % on C2); costs for coherent warps and for the
 // local-memory stack (C4: -3.5 %), which keep the branches.
+//
+// Leaf start (chains != nullptr and start != RT_REF_NONE): the ray leaves a primitive whose leaf is known.  The
+// leaf's box and the boxes of all its ancestors contain the origin, so the slab test accepts them for any
+// direction: they are skipped.  What remains to be tested are the siblings along the path; the host has copied
+// them, two by two, into "walk pairs" that look like any other pair of nodes (bvh_build.h).  The chain of the
+// leaf is pushed (root side first), traversal starts at the leaf itself and then pops the walk pairs from the
+// deepest up — the order the top-down traversal would have visited them in.  Skipping a box test can only add
+// candidates, never remove one, so the closest hit is unchanged (and so is every bit of the image).
 template <class Stack, bool COUNT, bool QUADS = false, bool PRED = false>
 RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sph,
                          const I2 *__restrict__ meta, uint32_t root_ref, V3 o, V3 d, float tmin,
                          float tmax, Stack &stack, HitRec &hit, WorkCounters *wc,
-                         const F4 *__restrict__ quads = nullptr) {
+                         const F4 *__restrict__ quads = nullptr, const uint32_t *__restrict__ chains = nullptr,
+                         uint32_t start = RT_REF_NONE) {
     const V3 inv = v3(cull_rcp(d.x), cull_rcp(d.y), cull_rcp(d.z));
     const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
     const V3 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
@@ -229,6 +238,11 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
     bool have_id = false; // best_id is loaded lazily: only exact ties need it
     stack.reset();
     uint32_t ref = root_ref;
+    if (chains != nullptr && start != RT_REF_NONE) {
+        const uint32_t len = chains[start];
+        for (uint32_t k = 1; k <= len; k++) stack.push(chains[start + k]);
+        ref = chains[start + len + 1];
+    }
     for (;;) {
         // "while-while": every lane first descends through inner nodes until it holds a leaf (or
         // nothing), then the lanes test their leaves together.  RT_REF_NONE has the leaf bit set.

@@ -31,7 +31,7 @@ void load(const rt_scene_desc *d, int max_leaf, float origin_radius, HostScene *
     compute_scene_center(s->prims, m, &ext, &surf);
     // derived radius as rt_scene_create + a camera / ray batch anywhere within the scene's extent
     float R = origin_radius > 0 ? origin_radius : (d->ray_origin_radius > 0 ? d->ray_origin_radius : (float)(2 * ext + surf));
-    build_flat_bvh(s->prims, R, max_leaf, &s->bvh);
+    build_flat_bvh(s->prims, R, max_leaf, &s->bvh, nullptr, true); // with the leaf-start chains, as the kernels get them
     pack_materials(d, &s->mats);
     s->images.resize(d->n_images);
     s->texels.resize(d->n_images);
@@ -90,7 +90,7 @@ uint64_t hs_bvh_hash(const rt_scene_desc *d, int max_leaf, float origin_radius, 
     uint64_t h = 1469598103934665603ull;
     const FlatBvh &b = s.bvh;
     h = fnv(h, b.nodes.data(), b.nodes.size() * sizeof(F4));
-    h = fnv(h, b.dev_nodes.data(), b.dev_nodes.size() * sizeof(F4));
+    h = fnv(h, b.dev_nodes.data(), b.nodes.size() * sizeof(F4)); // the tree's own nodes (the leaf-start walk pairs follow them)
     h = fnv(h, b.sph.data(), b.sph.size() * sizeof(F4));
     h = fnv(h, b.meta.data(), b.meta.size() * sizeof(I2));
     h = fnv(h, b.sph_prim.data(), b.sph_prim.size() * 4);
@@ -121,6 +121,36 @@ int hs_trace(const rt_scene_desc *d, int max_leaf, float origin_radius, const fl
     return 0;
 }
 
+// hs_trace with leaf start: ray i starts its traversal at the leaf of sphere slot start_slots[i] % n_slots (rt_trace.h).
+// A leaf's chain plus the leaf itself cover the whole tree, so ANY start slot must give the answer of the root start;
+// the work counters show what the right start saves.
+int hs_trace_leaf_start(const rt_scene_desc *d, int max_leaf, float origin_radius, const float *origins, const float *dirs,
+                        const uint32_t *start_slots, int64_t n, float tmin, float tmax, int32_t *id_out, float *t_out,
+                        uint64_t *box_tests, uint64_t *sphere_tests) {
+    HostScene s;
+    load(d, max_leaf, origin_radius, &s);
+    WorkCounters wc{0, 0};
+    const size_t n_slots = s.bvh.sph.size(), n_q = s.bvh.quad_prim.size();
+    for (int64_t i = 0; i < n; i++) {
+        LocalStack<64> stack;
+        HitRec h;
+        uint32_t start = RT_REF_NONE;
+        if (n_slots + n_q) {
+            const size_t k = start_slots[i] % (n_slots + n_q);
+            start = k < n_slots ? s.bvh.sph_chain[k] : s.bvh.quad_chain[k - n_slots];
+        }
+        trace_closest<LocalStack<64>, true, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref,
+                                                  v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+                                                  v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmin, tmax, stack, h, &wc,
+                                                  s.bvh.quad.data(), s.bvh.chains.data(), start);
+        if (h.slot == RT_REF_NONE) id_out[i] = -1, t_out[i] = 0;
+        else id_out[i] = slot_object_id(h.slot, s.bvh.meta.data(), s.bvh.quad.data()), t_out[i] = h.t;
+    }
+    if (box_tests) *box_tests = wc.box_tests;
+    if (sphere_tests) *sphere_tests = wc.sphere_tests;
+    return 0;
+}
+
 // The megakernel's per-path loop + reduce + resolve, serially, in the same operation order.
 int hs_render(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32_t sample_offset, int32_t sample_count,
               int32_t total_spp, int max_leaf, uint8_t *rgb_out, float *accum_out) {
@@ -136,16 +166,18 @@ int hs_render(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int32
             V3 o, dir;
             generate_ray(c, rng, (int)(pix % cam->width), (int)(pix / cam->width), o, dir);
             V3 thr = v3(1, 1, 1), rad = v3(0, 0, 0);
+            uint32_t start = RT_REF_NONE; // leaf start, as render_kernel: secondary rays start at the leaf they leave
             for (int depth = 0; depth < c.max_depth;) {
                 LocalStack<64> stack;
                 HitRec h;
                 trace_closest<LocalStack<64>, false, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(),
                                                            s.bvh.root_ref, o, dir, 0.001f, INFINITY, stack, h, nullptr,
-                                                           s.bvh.quad.data());
+                                                           s.bvh.quad.data(), s.bvh.chains.data(), start);
                 if (h.slot == RT_REF_NONE) {
                     rad = rad + thr * c.background;
                     break;
                 }
+                start = (h.slot & RT_HIT_QUAD) ? s.bvh.quad_chain[h.slot & ~RT_HIT_QUAD] : s.bvh.sph_chain[h.slot];
                 V3 atten, emitted;
                 bool sc = shade_at(s, h, rng, o, dir, atten, emitted);
                 rad = rad + thr * emitted;

@@ -47,7 +47,7 @@ struct Tree {
         return h.x * h.y + h.y * h.z + h.z * h.x;
     }
     void build() {
-        const size_t n_nodes = s->bvh.dev_nodes.size() / 2;
+        const size_t n_nodes = s->bvh.nodes.size() / 2; // the tree's own nodes (dev_nodes also holds the product's walk pairs)
         parent_node.assign(n_nodes / 2 + 1, -1);
         slot_leaf.assign(s->bvh.sph.size(), -1);
         node_depth.assign(n_nodes, 0);
@@ -120,6 +120,9 @@ struct Variant {
     int K;       // 2, 4, 8
     bool ls;     // leaf start
     bool walk1 = false; // binary leaf start: one sibling per walk step instead of two
+    bool nested = false; // walk steps run in their own loop after the leaf phase (no bookkeeping in the descend loop)
+    bool near = false;   // rays that leave a huge primitive start at the leaf of the small sphere nearest to their origin
+    int extra = 0;       // extra issue slots per merged inner step (walk/descend selection)
     const F4 *nodes() const { return t->s->bvh.dev_nodes.data(); }
     bool box(const Lane &l, int node, float &tn) const {
         return box_test(nodes()[2 * (size_t)node], nodes()[2 * (size_t)node + 1], l.inv, l.noi, l.ainv, 0.001f, l.tbest, tn);
@@ -133,14 +136,25 @@ struct Variant {
         l.stack.clear();
         l.up = -1;
         if (ls && r.start_slot != RT_REF_NONE) {
-            l.up = t->slot_leaf[r.start_slot];
+            uint32_t slot = r.start_slot;
+            if (near && fabsf(t->s->bvh.sph[slot].w) > 100) {
+                float bd = INFINITY;
+                for (size_t q = 0; q < t->s->bvh.sph.size(); q++) {
+                    const F4 &sp = t->s->bvh.sph[q];
+                    if (fabsf(sp.w) > 100) continue;
+                    const float dx = sp.x - r.o.x, dy = sp.y - r.o.y, dz = sp.z - r.o.z, dd = dx * dx + dy * dy + dz * dz;
+                    if (dd < bd) bd = dd, slot = (uint32_t)q;
+                }
+            }
+            l.up = t->slot_leaf[slot];
             l.ref = t->ref_of(l.up);
         } else {
             l.ref = t->s->bvh.root_ref;
         }
     }
     bool done(const Lane &l) const { return l.ref == RT_REF_NONE && l.up < 0; }
-    bool want_inner(const Lane &l) const { return !(l.ref & RT_LEAF) || (l.ref == RT_REF_NONE && l.up >= 0); }
+    bool want_inner(const Lane &l) const { return !(l.ref & RT_LEAF) || (!nested && l.ref == RT_REF_NONE && l.up >= 0); }
+    bool want_walk(const Lane &l) const { return nested && l.ref == RT_REF_NONE && l.up >= 0; }
     bool want_leaf(const Lane &l) const { return l.ref != RT_REF_NONE && (l.ref & RT_LEAF); }
     uint32_t pop(Lane &l) const {
         if (l.stack.empty()) return RT_REF_NONE;
@@ -227,13 +241,22 @@ Counters replay(const Variant &v, const std::vector<SPath> &paths, int width, in
                 if (!n) break;
                 for (int q = 0; q < width; q++)
                     if (lanes[q].alive && v.want_inner(lanes[q])) v.inner(lanes[q], c), lane_steps[q] += 1;
-                c.slots += step_cost, c.inner_slots += step_cost, c.inner_lane += n, c.inner_steps += 1;
+                c.slots += step_cost + v.extra, c.inner_slots += step_cost + v.extra, c.inner_lane += n, c.inner_steps += 1;
             }
             int mx = 0;
             for (auto &l : lanes)
                 if (l.alive && v.want_leaf(l)) mx = std::max(mx, v.leaf(l, c));
-            if (!mx) break;
-            c.slots += (width == 32 ? mx * COST_SPH : COST_SPH + 10) + COST_LEAF; // cooperative: one sphere per lane
+            if (mx) c.slots += (width == 32 ? mx * COST_SPH : COST_SPH + 10) + COST_LEAF; // cooperative: one sphere per lane
+            bool walked = false;
+            for (;;) { // nested walk loop: lanes whose stack ran dry test the next siblings on their path
+                int n = 0;
+                for (int q = 0; q < width; q++)
+                    if (lanes[q].alive && v.want_walk(lanes[q])) v.inner(lanes[q], c), lane_steps[q] += 1, n++;
+                if (!n) break;
+                walked = true;
+                c.slots += 45, c.inner_slots += 45, c.inner_lane += n, c.inner_steps += 1;
+            }
+            if (!mx && !walked) break;
         }
         int blocks = 0;
         for (auto &l : lanes) {
@@ -329,13 +352,19 @@ extern "C" int ts_run(const rt_scene_desc *d, const rt_camera *cam, uint64_t see
         bool ls;
         int width;
         bool walk1;
+        bool nested = false;
+        int extra = 0;
+        bool near = false;
     } cfgs[] = {{"bvh2", 2, false, 32, false},  {"bvh2-ls", 2, true, 32, false}, {"bvh2-ls1", 2, true, 32, true},
+                {"bvh2-ls+12", 2, true, 32, false, false, 12}, {"bvh2-ls-nest", 2, true, 32, false, true, 0},
+                {"bvh2-ls-near", 2, true, 32, false, false, 0, true}, {"bvh2-ls-near+3", 2, true, 32, false, false, 3, true},
                 {"bvh4", 4, false, 32, false},  {"bvh4-ls", 4, true, 32, false}, {"bvh8", 8, false, 32, false},
                 {"bvh8-ls", 8, true, 32, false}, {"coop8", 8, false, 4, false},  {"coop8-ls", 8, true, 4, false}};
     for (auto &cf : cfgs) {
-        Variant v{&t, cf.K, cf.ls, cf.walk1};
+        Variant v{&t, cf.K, cf.ls, cf.walk1, cf.nested, cf.near, cf.extra};
         const int step = cf.width == 4 ? 45 : (cf.K == 2 ? COST_PAIR : cost_wide(cf.K));
-        Counters r = replay(v, paths, cf.width, step, true, &expect);
+        // (a start leaf far from the origin may add a candidate the padded boxes cull: outside the envelope)
+        Counters r = replay(v, paths, cf.width, step, !cf.near, &expect);
         const double slots_per_ray = r.slots / r.rays; // warp issue slots per ray
         if (base == 0) base = slots_per_ray;
         printf("%-10s %9.1f %9.3f %9.2f %9.2f %9.2f %9.2f %8.1f%%\n", cf.name, slots_per_ray, slots_per_ray / base,

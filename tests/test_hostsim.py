@@ -327,3 +327,53 @@ def test_random_scenes_traversal_equals_world_hit(hs, orc, seed):
         assert np.array_equal(ids, rids), (seed, max_leaf, int((ids != rids).sum()))
         hit = rids >= 0
         assert np.array_equal(ts[hit].view(np.uint32), rts[hit].view(np.uint32))
+
+
+def hs_trace_leaf_start(hs, scene, o, d, start_slots, max_leaf=4, radius=0.0, tmin=0.001, tmax=np.inf):
+    desc, keep = scene.to_desc()
+    o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+    st_ = np.ascontiguousarray(start_slots, np.uint32)
+    ids, ts = np.empty(len(o), np.int32), np.empty(len(o), np.float32)
+    bt, st = C.c_uint64(), C.c_uint64()
+    hs.hs_trace_leaf_start(C.byref(desc), max_leaf, C.c_float(radius), o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                           st_.ctypes.data_as(C.c_void_p), C.c_int64(len(o)), C.c_float(tmin), C.c_float(tmax),
+                           ids.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p), C.byref(bt), C.byref(st))
+    return ids, ts, bt.value, st.value
+
+
+@pytest.mark.parametrize("max_leaf", [1, 4, 8])
+def test_leaf_start_from_any_leaf_equals_world_hit(hs, orc, random_scene, max_leaf):
+    """Leaf start (rt_trace.h): the chain of a leaf plus the leaf cover the whole tree, so the closest hit does not
+    depend on WHICH leaf a ray starts from — random start slots must reproduce World.Hit bit for bit."""
+    rng = np.random.default_rng(21)
+    n = 100_000
+    sp = random_scene.spheres
+    pick = rng.integers(0, len(sp), n)
+    c = np.stack([sp["cx"][pick], sp["cy"][pick], sp["cz"][pick]], -1)
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    o = (c + v * (np.minimum(sp["r"][pick], 3.0) * rng.choice([1.0, 1.0, 2.0, 0.5], n))[:, None]).astype(np.float32)
+    d = (rng.normal(size=(n, 3)) * rng.choice([0.2, 1, 9], n)[:, None]).astype(np.float32)
+    rids, rts = orc.trace(random_scene, o, d)
+    ids, ts, bt_any, _ = hs_trace_leaf_start(hs, random_scene, o, d, rng.integers(0, 1 << 30, n), max_leaf)
+    assert np.array_equal(ids, rids)
+    assert np.array_equal(ts[rids >= 0].view(np.uint32), rts[rids >= 0].view(np.uint32))
+
+
+def test_leaf_start_on_quads_and_fuzz_scenes(hs, orc):
+    from tests.fuzz_scenes import fuzz_scene_and_rays
+    rng = np.random.default_rng(5)
+    for seed in range(6):
+        s, o, d, radius = fuzz_scene_and_rays(seed, m=3000)
+        ids, ts, _, _ = hs_trace_leaf_start(hs, s, o, d, rng.integers(0, 1 << 30, len(o)), 4, radius)
+        rids, rts = orc.trace(s, o, d)
+        assert np.array_equal(ids, rids), seed
+        assert np.array_equal(ts[rids >= 0].view(np.uint32), rts[rids >= 0].view(np.uint32))
+    s = scenes.mixed_scene()
+    n = 20_000
+    o = rng.uniform(-4, 4, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    ids, ts, _, _ = hs_trace_leaf_start(hs, s, o, d, rng.integers(0, 1 << 30, n))
+    rids, rts = orc.trace(s, o, d)
+    assert np.array_equal(ids, rids)
+    assert np.array_equal(ts[rids >= 0].view(np.uint32), rts[rids >= 0].view(np.uint32))
