@@ -38,8 +38,9 @@ struct DevScene {
     uint32_t stack_depth; // entries per thread for the shared-memory stack
 };
 
+#define RT_SMEM_NODE_STRIDE 40 /* bytes per node in the shared-memory copy (rt_trace.h: NSTRIDE) */
 static size_t scene_smem_bytes(const DevScene &s) {
-    return (size_t)s.n_nodes * 32 + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 +
+    return (size_t)s.n_nodes * RT_SMEM_NODE_STRIDE + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 +
            (size_t)s.n_quad_slots * 16 * RT_QUAD_F4 + (size_t)s.n_slots * 8 +
            (s.chains ? ((size_t)s.n_chain_words + s.n_slots + s.n_quad_slots) * 4 : 0);
 }
@@ -62,7 +63,7 @@ __device__ __forceinline__ uint32_t chain_of_slot(const uint32_t *sph_chain, con
 
 __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned char *smem) {
     F4 *nodes = reinterpret_cast<F4 *>(smem);
-    F4 *sph = nodes + 2 * (size_t)sc.n_nodes;
+    F4 *sph = nodes + (size_t)sc.n_nodes * RT_SMEM_NODE_STRIDE / 16; // n_nodes is even: a whole number of F4
     F4 *mats = sph + sc.n_slots;
     F4 *quads = mats + 2 * (size_t)sc.n_mats;
     I2 *meta = reinterpret_cast<I2 *>(quads + (size_t)RT_QUAD_F4 * sc.n_quad_slots);
@@ -78,7 +79,7 @@ __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned ch
     const uint4 *src;
     uint4 *dst;
     src = reinterpret_cast<const uint4 *>(sc.nodes), dst = reinterpret_cast<uint4 *>(nodes);
-    for (uint32_t i = threadIdx.x; i < 2 * sc.n_nodes; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (uint32_t i = threadIdx.x; i < 2 * sc.n_nodes; i += blockDim.x) dst[i + (i >> 2)] = __ldg(src + i); // 4 F4 per pair -> 5
     src = reinterpret_cast<const uint4 *>(sc.sph), dst = reinterpret_cast<uint4 *>(sph);
     for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) dst[i] = __ldg(src + i);
     src = reinterpret_cast<const uint4 *>(sc.mats), dst = reinterpret_cast<uint4 *>(mats);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 
         // ---- one path segment: ray.go:32-54 unrolled front to back ----
         HitRec h;
-        trace_closest<Stack, COUNT, QUADS, SMEM>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+        trace_closest<Stack, COUNT, QUADS, SMEM, SMEM ? RT_SMEM_NODE_STRIDE : 32>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
                                                  chains, start);
         n_rays++;
         bool done;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 }
             }
             HitRec h;
-            trace_closest<Stack, COUNT, QUADS>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+            trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
                                                FIRST ? nullptr : chains, start);
             n_rays++;
             hit_slot = h.slot;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ De
         const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         HitRec h;
-        trace_closest<Stack, false, QUADS>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, quads);
+        trace_closest<Stack, false, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, quads);
         if (h.slot == RT_REF_NONE) {
             id_out[i] = -1, t_out[i] = 0.0f;
         } else {
