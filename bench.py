@@ -183,6 +183,7 @@ def main():
                          "tile: interleaved scanlines at world*spp samples (weak scaling, no reduction)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,9 +259,12 @@ def main():
     e0.record(stream)
     rays = mk_ms = 0.0
     launches = mk_launches = 0
+    work_bytes = survivors = 0
     for _ in range(args.steps):
         st, rgb = step()
         rays += st.rays
+        work_bytes += st.work_bytes
+        survivors += st.survivors
         mk_ms += st.ms_megakernel
         launches += st.kernel_launches + (1 if rank == 0 else 0)
         mk_launches += st.megakernel_launches
@@ -307,22 +311,89 @@ def main():
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t[0]) * 1e3,
                "what": "rt_scene_create (host BVH build + upload) + rt_render (RGB8 to host) + rt_scene_destroy per step"}
 
+    # ---- strong scaling sub-record (BASELINE config C5's plan on this config): the SAME frame, its spp divided over
+    # the ranks, one NCCL reduce; t1 = the whole frame on rank 0 alone, timed in this process, so the efficiency
+    # t1 / (N * tN) compares like with like.  e2e = scene upload + render of the rank's sample range + reduce +
+    # RGB8 to the host, per step, wall clock. ----
+    strong = None
+    if args.split == "weak" and not args.no_strong:
+        so, sspp, stot = sharding.sample_split_strong(rank, world, cam.spp)
+
+        def strong_step(scene_handle, offset, count, everyone=True):
+            if count > 0:
+                scene_handle.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=offset, sample_count=count)
+            else:
+                accum.zero_()
+            full = sharding.reduce_accumulators(accum, dst=0) if everyone else accum
+            if rank == 0:
+                return api.resolve_device(full.data_ptr(), W, H, stot, local_rank, stream.cuda_stream)
+
+        def timed(fn, n):
+            fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record(stream)
+            for _ in range(n):
+                fn()
+            b.record(stream)
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / n, (time.perf_counter() - t0) * 1e3 / n], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0]), float(t[1])
+        n_strong = max(1, min(args.steps, 5))
+        tn_ms, _ = timed(lambda: strong_step(sc, so, sspp), n_strong)
+        if world > 1:   # the whole frame on rank 0 alone (the other ranks wait at the barrier)
+            t1_ms, _ = timed(lambda: strong_step(sc, 0, cam.spp, everyone=False) if rank == 0 else None, n_strong)
+        else:
+            t1_ms = tn_ms
+
+        def strong_e2e_step():
+            with api.Scene(scene_data, local_rank) as s2:
+                s2.set_stream(stream.cuda_stream)
+                strong_step(s2, so, sspp)
+        _, e2e_ms = timed(strong_e2e_step, max(1, min(args.steps, 3)))
+        frame = n_pix * cam.spp
+        strong = {"what": f"the {cam.spp}-spp frame divided over {world} GPU(s) (sample-split, one NCCL reduce)",
+                  "value": frame / (tn_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": tn_ms,
+                  "ms_per_step_1gpu": t1_ms, "efficiency_vs_1gpu": t1_ms / (world * tn_ms),
+                  "e2e": {"value": frame / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
+                          "h2d_bytes_per_step": int(scene_data.nbytes() + 256), "d2h_bytes_per_step": int(n_pix * 3)},
+                  "spp_per_gpu": [sharding.sample_split_strong(r, world, cam.spp)[1] for r in range(world)]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- algorithmic work per sample, counted by the instrumented kernel on the same workload
-    # at a reduced spp (per-ray statistics do not depend on spp) ----
+    # ---- algorithmic work per sample, counted by the instrumented kernels on the same workload at a
+    # reduced spp (per-ray statistics do not depend on spp).  The roofline's numerator is the work of the plain
+    # top-down traversal of the binary tree — round 1's definition, 1 755 lane-instr/sample on C2 — counted on a
+    # scene handle built WITHOUT the leaf-start chains; what today's kernels execute (fewer box tests: leaf start
+    # skips the ancestors of the leaf a ray leaves) is reported next to it as `executed`. ----
     cnt_spp = max(1, min(spp, 4))
-    stc = sc.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=0, sample_count=cnt_spp,
-                                 flags=1, rows=rows)
-    n_box = stc.box_tests / stc.rays
-    n_sph = stc.sphere_tests / stc.rays
-    n_hit = stc.hits / stc.rays
-    seg = stc.rays / stc.samples
-    instr_per_sample = F_GEN + seg * (n_box * F_BOX + n_sph * F_SPH + n_hit * (F_HIT + F_SHADE))
-    bytes_per_ray = n_box * B_BOX + n_sph * B_SPH + n_hit * B_HIT
+
+    def count_work(scene_handle):
+        stc = scene_handle.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=0,
+                                               sample_count=cnt_spp, flags=1, rows=rows)
+        n_box, n_sph, n_hit = stc.box_tests / stc.rays, stc.sphere_tests / stc.rays, stc.hits / stc.rays
+        seg = stc.rays / stc.samples
+        return {"instr_per_sample": F_GEN + seg * (n_box * F_BOX + n_sph * F_SPH + n_hit * (F_HIT + F_SHADE)),
+                "segments_per_sample": seg, "box_tests_per_ray": n_box, "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit,
+                "bytes_per_ray": n_box * B_BOX + n_sph * B_SPH + n_hit * B_HIT}
+    executed = count_work(sc)
+    prev = os.environ.get("RT_B200_LEAF_START")
+    os.environ["RT_B200_LEAF_START"] = "0"
+    with api.Scene(scene_data, local_rank) as sc_ref:
+        sc_ref.set_stream(stream.cuda_stream)
+        algo = count_work(sc_ref)
+    if prev is None:
+        del os.environ["RT_B200_LEAF_START"]
+    else:
+        os.environ["RT_B200_LEAF_START"] = prev
+    instr_per_sample, seg = algo["instr_per_sample"], algo["segments_per_sample"]
+    bytes_per_ray = algo["bytes_per_ray"]
     peaks, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     peak_instr = sm_count * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12  # T lane-instr/s
@@ -330,24 +401,27 @@ def main():
     samples_per_launch = samples_per_rank * args.steps / max(1, mk_launches)
     achieved = instr_per_sample * samples_per_launch / (mk_ms_per_launch * 1e-3) / 1e12
     smem_bw = bytes_per_ray * (rays / world / args.steps) / (mk_ms / args.steps * 1e-3) / 1e9
+    work_bytes_per_launch = work_bytes / max(1, mk_launches)
     roofline = {
         "bound": "fp32_issue", "kernel": "primary_stage_kernel + render_kernel<SPLIT> (timed together, per pass)",
         "achieved": achieved, "peak": peak_instr,
         "unit": "T lane-instr/s", "frac": achieved / peak_instr,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one C2 pass (66.42 M paths = 82 spp x 810 000 px):
-        # primary_stage_kernel 2.784 GB + render_kernel<SPLIT> 3.596 GB, ncu --set full,
-        # profiles/r01bc_kernels_ncu_full.txt.  Algorithmic: a 16-byte radiance record per path plus a
-        # 48-byte queue entry written and read once per path that survives its first segment (83 %).
-        "traffic": 6.380e9 * samples_per_launch / 66.42e6
-        if args.config == "C2" and not args.width else None,
-        "traffic_detail": {"unit": "bytes of DRAM traffic per pass (both kernels), scaled from the profiled 66.42 M-path pass "
-                                   "to this run's average pass size",
-                           "profiled_bytes": 6.380e9, "profiled_paths": 66.42e6,
-                           "algorithmic_bytes": (16 + 96 * 0.83) * samples_per_launch,
-                           "source": "profiles/r01bc_kernels_ncu_full.txt (C2 pass: 82 spp x 1200x675 = 66.42 M paths)"},
+        # HBM bytes per pass (both kernels + the ordered reduce), from this run's own counters (rt_stats.work_bytes):
+        # a 16-byte radiance record written and read per path, a 48-byte queue entry written and read per path that
+        # survives its first segment, the accumulator read + written per pass.  ncu's dram__bytes of the profiled
+        # pass agrees within 1 % (profiles/r02*_kernels_ncu_full.txt).
+        "traffic": work_bytes_per_launch,
+        "traffic_detail": {"unit": "bytes of HBM traffic per pass, derived from the run's counters",
+                           "survivors_per_sample": survivors / max(1.0, samples_per_rank * args.steps),
+                           "framebuffer_bytes": n_pix * 12,
+                           "note": "SURVEY §8d's algorithmic HBM bytes for this regime are the framebuffer alone; the rest is "
+                                   "the design's per-path radiance record + survivor queue"},
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz {peaks['sm_max_mhz']:.0f} ({peak_src} MEASURED_PEAKS.json clock)",
-        "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": n_box,
-        "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit, "counted_at_spp": cnt_spp,
+        "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": algo["box_tests_per_ray"],
+        "sphere_tests_per_ray": algo["sphere_tests_per_ray"], "hit_fraction": algo["hit_fraction"], "counted_at_spp": cnt_spp,
+        "numerator": "top-down traversal of the binary tree (round 1's definition); `executed` = what the leaf-start kernels run",
+        "executed": {k: executed[k] for k in ("instr_per_sample", "box_tests_per_ray", "sphere_tests_per_ray")},
+        "frac_executed": executed["instr_per_sample"] / instr_per_sample * achieved / peak_instr,
         "ms_per_launch": mk_ms_per_launch, "launches": mk_launches,
         "kernel_share_of_step": mk_ms / dev_ms if world == 1 else None,
         # BVH-fetch regime: algorithmic bytes/ray x rays/s.  Served from shared memory when the
@@ -355,9 +429,9 @@ def main():
         "scene_bytes_per_ray": bytes_per_ray, "scene_fetch_gbs": smem_bw,
         "scene_in_shared_memory": bool(sc.bvh_info().in_shared_memory),
         "scene_fetch_vs_hbm_peak": smem_bw / peaks["hbm_gbs"],
-        "hbm": {"note": "HBM carries only the per-sample radiance buffer (16 B written + 16 B read per sample) "
-                        "and the framebuffer; the scene is staged in shared memory",
-                "achieved": 32.0 * samples_per_rank / (ms_per_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"},
+        "hbm": {"note": "HBM carries the per-pass work buffers (radiance records, survivor queue) and the framebuffer; "
+                        "the scene is staged in shared memory",
+                "achieved": work_bytes / args.steps / (ms_per_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"},
     }
 
     cpu = None
@@ -376,6 +450,7 @@ def main():
         "config": config_dict(args, cam_opts, scene_data, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "wall_ms_per_step": wall_ms / args.steps,
+        "strong": strong,
     }
     print(json.dumps(line), flush=True)
     sc.close()

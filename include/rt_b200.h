@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 4
+#define RT_B200_ABI_VERSION 5
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -203,6 +203,10 @@ typedef struct rt_stats {
     uint32_t megakernel_launches; /* render_kernel launches among kernel_launches            */
     float ms_megakernel;          /* summed device time of the render_kernel launches alone   */
     uint32_t reserved;
+    uint64_t survivors;    /* paths that outlived their first segment (two-stage mode: queue entries)  */
+    uint64_t work_bytes;   /* HBM bytes the call's work buffers carry by construction: a 16-byte radiance
+                              record written and read per path, a 48-byte queue entry written and read per
+                              survivor, the accumulator read and written once per pass                    */
 } rt_stats;
 
 typedef struct rt_scene rt_scene; /* opaque */

@@ -5,7 +5,7 @@ sizes/offsets against the compiled library's view where that is observable.
 """
 import ctypes as C
 
-RT_B200_ABI_VERSION = 4
+RT_B200_ABI_VERSION = 5
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1
@@ -89,7 +89,8 @@ class rt_stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("box_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("hits", C.c_uint64), ("ms_render", C.c_float),
                 ("ms_total", C.c_float), ("kernel_launches", C.c_uint32),
-                ("megakernel_launches", C.c_uint32), ("ms_megakernel", C.c_float), ("reserved", C.c_uint32)]
+                ("megakernel_launches", C.c_uint32), ("ms_megakernel", C.c_float), ("reserved", C.c_uint32),
+                ("survivors", C.c_uint64), ("work_bytes", C.c_uint64)]
 
 
 class rt_bvh_info(C.Structure):

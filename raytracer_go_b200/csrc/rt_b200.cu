@@ -449,7 +449,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
     }
     RC(scene_alloc(&s->d_counter, sizeof(unsigned int), device, s->stream));
     RC(scene_alloc(&s->d_queue_count, RT_MAX_STAGES * sizeof(unsigned int), device, s->stream));
-    RC(scene_alloc(&s->d_stats, 4 * sizeof(unsigned long long), device, s->stream));
+    RC(scene_alloc(&s->d_stats, RT_N_STATS * sizeof(unsigned long long), device, s->stream));
     CU(cudaStreamSynchronize(s->stream));
 
     s->dev.nodes = s->d_nodes, s->dev.sph = s->d_sph, s->dev.meta = s->d_meta, s->dev.mats = s->d_mats;
@@ -741,7 +741,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     rc = ws_reserve(ws.samples, ws.samples_cap, need);
     if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, (s->n_stages > 1 ? 6 : 3) * need);
     if (rc != RT_OK) return rc;
-    CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), s->stream));
+    CU(cudaMemsetAsync(s->d_stats, 0, RT_N_STATS * sizeof(unsigned long long), s->stream));
 
     if (cam->max_depth <= 0) { // ray.go:33-35: every sample is black
         CU(cudaMemsetAsync(d_accum, 0, (size_t)n_pix * 3 * sizeof(float), s->stream));
@@ -765,6 +765,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.queue_d = p.queue_t = nullptr, p.queue_count = s->d_queue_count;
     p.in_o = p.in_d = p.in_t = nullptr, p.in_count = nullptr, p.stage_depth = 0;
     const bool balance = env_int("RT_B200_PASS_BALANCE", 0) != 0;
+    uint64_t n_passes_total = 0;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
         const uint32_t np = std::min(pix_tile, n_pix - pb);
         // RT_B200_PASS_BALANCE=1 makes the passes equal (500 spp at 82 per pass = 7 passes of 71-72 instead of
@@ -789,14 +790,17 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
             reduce_kernel<<<(np + 127) / 128, 128, 0, s->stream>>>(ws.samples, d_accum, pb, np, sp, k0 == 0);
             CU(cudaGetLastError());
             *launches += s->use_split ? 2 + s->n_stages : 2;
+            n_passes_total++;
         }
     }
     if (stats) {
-        unsigned long long h[4];
+        unsigned long long h[RT_N_STATS];
         CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         stats->samples = (uint64_t)n_pix * (uint64_t)spp;
         stats->rays = h[0], stats->hits = h[1], stats->box_tests = h[2], stats->sphere_tests = h[3];
+        stats->survivors = h[4];
+        stats->work_bytes = 32ull * stats->samples + 96ull * h[4] + 24ull * (uint64_t)n_pix * n_passes_total;
         float total = 0;
         for (size_t e = 2; e < n_ev; e += 2) {
             float ms = 0;
@@ -1101,6 +1105,7 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
         for (auto &j : jobs) {
             stats->samples += j.st.samples, stats->rays += j.st.rays, stats->hits += j.st.hits;
             stats->box_tests += j.st.box_tests, stats->sphere_tests += j.st.sphere_tests;
+            stats->survivors += j.st.survivors, stats->work_bytes += j.st.work_bytes;
             stats->kernel_launches += j.st.kernel_launches, stats->megakernel_launches += j.st.megakernel_launches;
             stats->ms_render = std::max(stats->ms_render, j.st.ms_render);
             stats->ms_megakernel = std::max(stats->ms_megakernel, j.st.ms_megakernel);

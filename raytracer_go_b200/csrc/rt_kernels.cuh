@@ -46,6 +46,7 @@ static size_t scene_smem_bytes(const DevScene &s) {
 }
 
 #define RT_LOCAL_STACK 64
+#define RT_N_STATS 6 /* device counters: rays, hits, box tests, sphere tests, survivors, (spare) */
 
 // Stage the scene arrays in shared memory (LDG.128 -> STS.128), return the carved pointers.
 struct SmemScene {
@@ -116,7 +117,7 @@ struct RenderParams {
     uint32_t total_paths;  // n_pixels_pass * spp_pass
     float4 *samples;       // [total_paths] radiance of path (pixel - pixel_begin) * spp_pass + k
     unsigned int *counter; // next unclaimed path index
-    unsigned long long *stats; // rays, hits, box tests, sphere tests
+    unsigned long long *stats; // rays, hits, box tests, sphere tests, survivors (RT_N_STATS)
     uint64_t div_spp, div_width; // fast_div multipliers of spp_pass and cam.width (host: fast_div_magic)
     uint32_t regen_min;    // regenerate only when at least this many lanes of the warp are idle
     uint32_t chunk;        // work items a warp claims per atomic (RT_CHUNK by default)
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
     bool exhausted = false;
     // work items: all paths of the pass, or (two-stage mode) the survivors queued by the primary stage
     const uint32_t total_items = SPLIT ? *p.queue_count : p.total_paths;
+    if (SPLIT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.stats + 4, (unsigned long long)total_items);
 
     bool alive = false;
     uint32_t idx = 0;

@@ -63,17 +63,17 @@ for step in "$@"; do
       var=$(echo "$step" | cut -d: -f2); vals=$(echo "$step" | cut -d: -f3 | tr ',' ' ')
       cfgs=$(echo "$step" | cut -d: -f4 | tr ',' ' '); [ -z "$cfgs" ] && cfgs=C2
       for v in $vals; do for cfg in $cfgs; do
-        env $var=$v timeout 600 python bench.py --config $cfg --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_sweep_${var}_${v}_${cfg}.json 2>> gpurun_out/${TAG}_sweep.err
+        env $var=$v timeout 600 python bench.py --config $cfg --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-strong > gpurun_out/${TAG}_sweep_${var}_${v}_${cfg}.json 2>> gpurun_out/${TAG}_sweep.err
         line "$var=$v" gpurun_out/${TAG}_sweep_${var}_${v}_${cfg}.json
       done; done ;;
     ncu-launches)
-      CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+      CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-strong"
       $CMD > gpurun_out/${TAG}_plain.log 2>&1 && \
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
       say "ncu-launches rc=$?" ;;
     ncu-full*)
       spp=$(echo "$step" | cut -s -d: -f2); [ -z "$spp" ] && spp=82
-      CMD="python bench.py --spp $spp --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+      CMD="python bench.py --spp $spp --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-strong"
       $CMD > gpurun_out/${TAG}_plain_full.log 2>&1 && \
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_kernel|primary_stage" -s 2 -c 2 -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
       say "ncu-full rc=$?" ;;
