@@ -136,8 +136,21 @@ struct Rng {
         ctr[0] = pixel, ctr[1] = sample, ctr[2] = 0, ctr[3] = 0;
         key[0] = (uint32_t)seed, key[1] = (uint32_t)(seed >> 32);
     }
+    // Reference pin (tests/test_pin_from_go.py): instead of Philox, hand out the uniforms of a caller-supplied list,
+    // four per block, so that the real Go code (fed the same values through a stub rand.Source) and this restatement
+    // see identical draws.  An exhausted list repeats its last value.
+    const float *feed = nullptr;
+    int64_t feed_n = 0, feed_pos = 0;
+    Rng(const float *values, int64_t n) : feed(values), feed_n(n) {
+        ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0, key[0] = key[1] = 0;
+    }
     // rand.Float32() is uniform on [0,1) (camera.go:290); 24 random mantissa bits.
     Block next() {
+        if (feed) {
+            Block b;
+            for (int i = 0; i < 4; i++, feed_pos++) b.u[i] = feed_n ? feed[std::min(feed_pos, feed_n - 1)] : 0.0f;
+            return b;
+        }
         uint32_t w[4];
         philox4x32_10(ctr, key, w);
         ctr[2]++;
@@ -924,6 +937,51 @@ int orc_scatter(const rt_scene_desc *desc, const float *origin, const float *dir
     float v[10] = {ok ? 1.0f : 0.0f, s.ray.origin.x, s.ray.origin.y, s.ray.origin.z, s.ray.dir.x,
                    s.ray.dir.y, s.ray.dir.z, s.attenuation.x, s.attenuation.y, s.attenuation.z};
     memcpy(out10, v, sizeof v);
+    return 0;
+}
+
+// Reference pin: Material.Scatter at the World.Hit of the ray with the uniforms of `feed` (four per block, layout at
+// struct Rng) instead of the Philox stream.  out10 as orc_scatter, out3 = Material.Emit at the hit.
+int orc_scatter_fed(const rt_scene_desc *desc, const float *origin, const float *dir, const float *feed,
+                    int64_t n_feed, float *out10, float *emit3) {
+    Scene sc;
+    if (!load_scene(desc, &sc)) return -1;
+    HitInfo hi{};
+    Ray r{ld3(origin), ld3(dir)};
+    if (!world_hit(sc, r, Interval{T_MIN, std::numeric_limits<float>::infinity()}, &hi)) return 1;
+    Rng rng(feed, n_feed);
+    Scatter s{};
+    const rt_material &m = sc.materials[sc.material_of(hi.object)];
+    bool ok = material_scatter(sc, m, r, hi, rng, &s);
+    V3 e = material_emit(sc, m, hi);
+    float v[10] = {ok ? 1.0f : 0.0f, s.ray.origin.x, s.ray.origin.y, s.ray.origin.z, s.ray.dir.x,
+                   s.ray.dir.y, s.ray.dir.z, s.attenuation.x, s.attenuation.y, s.attenuation.z};
+    memcpy(out10, v, sizeof v);
+    emit3[0] = e.x, emit3[1] = e.y, emit3[2] = e.z;
+    return 0;
+}
+
+// Reference pin: Ray.GetColor (ray.go:32-54) for an explicit ray, uniforms from `feed`.
+int orc_get_color_fed(const rt_scene_desc *desc, const float *origin, const float *dir, const float *background,
+                      int max_depth, int order, const float *feed, int64_t n_feed, float *out3) {
+    Scene sc;
+    if (!load_scene(desc, &sc)) return -1;
+    World w{&sc, nullptr};
+    Rng rng(feed, n_feed);
+    Ray r{ld3(origin), ld3(dir)};
+    V3 c = order == ORDER_ITERATIVE ? get_color_iterative(w, r, ld3(background), max_depth, rng)
+                                    : get_color_recursive(w, r, ld3(background), max_depth, rng);
+    out3[0] = c.x, out3[1] = c.y, out3[2] = c.z;
+    return 0;
+}
+
+// Reference pin: Camera.GetRay (camera.go:265-299) for pixel (i, j), uniforms from `feed`.
+int orc_get_ray_fed(const rt_camera *cam, int i, int j, const float *feed, int64_t n_feed, float *origin3, float *dir3) {
+    if (!cam) return -1;
+    Rng rng(feed, n_feed);
+    Ray r = get_ray(*cam, rng, i, j);
+    origin3[0] = r.origin.x, origin3[1] = r.origin.y, origin3[2] = r.origin.z;
+    dir3[0] = r.dir.x, dir3[1] = r.dir.y, dir3[2] = r.dir.z;
     return 0;
 }
 

@@ -63,6 +63,12 @@ def lib():
         L.orc_encode_pixel.restype = None
         L.orc_scatter.argtypes = [C.POINTER(abi.rt_scene_desc), C.c_void_p, C.c_void_p, C.c_uint64,
                                   C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_scatter_fed.argtypes = [C.POINTER(abi.rt_scene_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p]
+        L.orc_get_color_fed.argtypes = [C.POINTER(abi.rt_scene_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_get_ray_fed.argtypes = [C.POINTER(abi.rt_camera), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p]
         L.orc_primary_rays.argtypes = [C.POINTER(abi.rt_camera), C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_render.argtypes = [C.POINTER(abi.rt_scene_desc), C.POINTER(abi.rt_camera), C.c_uint64,
@@ -180,6 +186,33 @@ def scatter(scene, origin, direction, seed=1, pixel=0, sample=0):
         return None
     return dict(scattered=bool(out[0]), origin=out[1:4].copy(), dir=out[4:7].copy(),
                 attenuation=out[7:10].copy())
+
+
+def scatter_fed(scene, origin, direction, feed):
+    """Material.Scatter + Emit at the World.Hit of the ray, uniforms from `feed` (four per block) -> None or dict."""
+    desc, keep = scene.to_desc()
+    out, emit = np.zeros(10, np.float32), np.zeros(3, np.float32)
+    o, d, f = _f32(origin), _f32(direction), _f32(feed)
+    rc = lib().orc_scatter_fed(C.byref(desc), _p(o), _p(d), _p(f), len(f), _p(out), _p(emit))
+    if rc != 0:
+        return None
+    return dict(scattered=bool(out[0]), origin=out[1:4].copy(), dir=out[4:7].copy(), attenuation=out[7:10].copy(),
+                emitted=emit)
+
+
+def get_color_fed(scene, origin, direction, background, max_depth, feed, order=ORDER_RECURSIVE):
+    """Ray.GetColor (ray.go:32-54) for an explicit ray, uniforms from `feed`."""
+    desc, keep = scene.to_desc()
+    out = np.zeros(3, np.float32)
+    o, d, b, f = _f32(origin), _f32(direction), _f32(background), _f32(feed)
+    assert lib().orc_get_color_fed(C.byref(desc), _p(o), _p(d), _p(b), max_depth, order, _p(f), len(f), _p(out)) == 0
+    return out
+
+
+def get_ray_fed(cam, i, j, feed):
+    o, d, f = np.zeros(3, np.float32), np.zeros(3, np.float32), _f32(feed)
+    assert lib().orc_get_ray_fed(C.byref(cam), i, j, _p(f), len(f), _p(o), _p(d)) == 0
+    return o, d
 
 
 def primary_rays(cam, seed, pixel_begin, n_pixels, sample_offset=0, sample_count=1):

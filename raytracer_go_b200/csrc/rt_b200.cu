@@ -183,6 +183,7 @@ struct rt_scene {
     DevImage *d_images = nullptr;
     DevPerlin *d_perlins = nullptr;
     std::vector<uint16_t *> d_texels;
+    uint32_t n_images = 0, n_perlins = 0;
     int grid_cache[2] = {0, 0};  // persistent grid size of the plain / counting megakernel
     size_t smem_cache[2] = {0, 0};
     unsigned int *d_counter = nullptr;
@@ -457,6 +458,7 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
     s->dev.quads = s->d_quads, s->dev.n_quad_slots = (uint32_t)n_qslots;
     s->dev.root_ref = s->bvh.root_ref;
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
+    s->n_images = desc->n_images, s->n_perlins = desc->n_perlins;
     s->dev.stack_depth = s->bvh.max_depth + 2;
     if (s->dev.stack_depth > RT_LOCAL_STACK) // cannot happen: the builder balances the tree below depth 30
         return fail(RT_ERR_INTERNAL, "BVH depth %u exceeds the traversal stack (%d)", s->bvh.max_depth, RT_LOCAL_STACK);
@@ -554,6 +556,36 @@ static double dist_to_center(const rt_scene *s, const float *p) {
     double dx = p[0] - s->center[0], dy = p[1] - s->center[1], dz = p[2] - s->center[2];
     return std::sqrt(dx * dx + dy * dy + dz * dz);
 }
+
+// ---------------------------------------------------------------------------------------------
+// debug build (rt_debug.h): array sizes to the device before a call, violation counters back after it
+// ---------------------------------------------------------------------------------------------
+#if RT_DEBUG_CHECKS
+static int dbg_begin(rt_scene *s, size_t queue_cap, size_t samples_cap, size_t n_pixels, size_t n_images, size_t n_perlins) {
+    DbgBounds b;
+    b.n_nodes = s->dev.n_nodes, b.n_slots = s->dev.n_slots, b.n_quad_slots = s->dev.n_quad_slots, b.n_mats = s->dev.n_mats;
+    b.n_chain_words = s->dev.n_chain_words, b.stack_entries = s->use_smem ? s->dev.stack_depth : RT_LOCAL_STACK;
+    b.n_images = (uint32_t)n_images, b.n_perlins = (uint32_t)n_perlins;
+    b.queue_cap = queue_cap, b.samples_cap = samples_cap, b.n_pixels = n_pixels;
+    if (env_int("RT_B200_DEBUG_TRIP", 0)) b.stack_entries = 1; // self-test: proves the checks are live (tests/test_gpu_debug_build.py)
+    static const unsigned int zero[RT_DBG_N] = {0};
+    CU(cudaMemcpyToSymbolAsync(g_dbg_bounds, &b, sizeof b, 0, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyToSymbolAsync(g_dbg_violations, zero, sizeof zero, 0, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream)); // `b` is a local
+    return RT_OK;
+}
+static int dbg_end(rt_scene *s) {
+    unsigned int v[RT_DBG_N];
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpyFromSymbol(v, g_dbg_violations, sizeof v, 0, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < RT_DBG_N; k++)
+        if (v[k]) return fail(RT_ERR_INTERNAL, "debug build: bounds check '%s' failed %u time(s)", rt_dbg_names[k], v[k]);
+    return RT_OK;
+}
+#else
+static inline int dbg_begin(rt_scene *, size_t, size_t, size_t, size_t, size_t) { return RT_OK; }
+static inline int dbg_end(rt_scene *) { return RT_OK; }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // launches
@@ -742,6 +774,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, (s->n_stages > 1 ? 6 : 3) * need);
     if (rc != RT_OK) return rc;
     CU(cudaMemsetAsync(s->d_stats, 0, RT_N_STATS * sizeof(unsigned long long), s->stream));
+    RC(dbg_begin(s, need, need, n_pix, s->n_images, s->n_perlins));
 
     if (cam->max_depth <= 0) { // ray.go:33-35: every sample is black
         CU(cudaMemsetAsync(d_accum, 0, (size_t)n_pix * 3 * sizeof(float), s->stream));
@@ -793,6 +826,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
             n_passes_total++;
         }
     }
+    RC(dbg_end(s));
     if (stats) {
         unsigned long long h[RT_N_STATS];
         CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
@@ -1164,8 +1198,11 @@ static int rt_trace_impl(rt_scene *scene, const float *origins, const float *dir
         cleanup();
         return fail(e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA, "rt_trace setup: %s", cudaGetErrorString(e));
     }
-    rc = scene->has_quads ? launch_trace_t<256, true>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t)
-                          : launch_trace_t<256, false>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t);
+    rc = dbg_begin(scene, 0, 0, 0, scene->n_images, scene->n_perlins);
+    if (rc == RT_OK)
+        rc = scene->has_quads ? launch_trace_t<256, true>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t)
+                              : launch_trace_t<256, false>(scene, d_o, d_d, n, tmin, tmax, d_id, d_t);
+    if (rc == RT_OK) rc = dbg_end(scene);
     if (rc == RT_OK) {
         e = cudaMemcpyAsync(id_out, d_id, (size_t)n * 4, cudaMemcpyDeviceToHost, scene->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(t_out, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, scene->stream);

@@ -39,6 +39,14 @@ struct DevScene {
 };
 
 #define RT_SMEM_NODE_STRIDE 40 /* bytes per node in the shared-memory copy (rt_trace.h: NSTRIDE) */
+// Shared-memory pairs transposed for FFMA2 (rt_trace.h: box_test_pair): 0 never, 1 always, 2 (default) only in the
+// instantiations with quads.  Measured (profiles/r02h): the 9 FFMA2 of a pair cost what the 18 FFMA they replace do
+// (a 64-bit operand read takes two issue cycles), so the sphere scenes gain nothing (C2 -1.5 %, C3 -0.8 %); the
+// Cornell box, whose leaves run the longer quad test, gains 3.9 %.
+#ifndef RT_PACKED_PAIRS
+#define RT_PACKED_PAIRS 2
+#endif
+#define RT_PACKED(SMEM, QUADS) ((SMEM) && (RT_PACKED_PAIRS == 1 || (RT_PACKED_PAIRS == 2 && (QUADS))))
 static size_t scene_smem_bytes(const DevScene &s) {
     return (size_t)s.n_nodes * RT_SMEM_NODE_STRIDE + (size_t)s.n_slots * 16 + (size_t)s.n_mats * 32 +
            (size_t)s.n_quad_slots * 16 * RT_QUAD_F4 + (size_t)s.n_slots * 8 +
@@ -62,6 +70,7 @@ __device__ __forceinline__ uint32_t chain_of_slot(const uint32_t *sph_chain, con
     return (slot & RT_HIT_QUAD) ? quad_chain[slot & ~RT_HIT_QUAD] : sph_chain[slot];
 }
 
+template <bool PACKED>
 __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned char *smem) {
     F4 *nodes = reinterpret_cast<F4 *>(smem);
     F4 *sph = nodes + (size_t)sc.n_nodes * RT_SMEM_NODE_STRIDE / 16; // n_nodes is even: a whole number of F4
@@ -80,7 +89,18 @@ __device__ __forceinline__ SmemScene stage_scene(const DevScene &sc, unsigned ch
     const uint4 *src;
     uint4 *dst;
     src = reinterpret_cast<const uint4 *>(sc.nodes), dst = reinterpret_cast<uint4 *>(nodes);
+    if constexpr (PACKED) {
+    // one thread per pair of sibling nodes: (cL, refL)(hL)(cR, refR)(hR) -> the transposed form box_test_pair reads
+    for (uint32_t i = threadIdx.x; i < sc.n_nodes / 2; i += blockDim.x) {
+        const uint4 cl = __ldg(src + 4 * i), hl = __ldg(src + 4 * i + 1), cr = __ldg(src + 4 * i + 2), hr = __ldg(src + 4 * i + 3);
+        dst[5 * i + 0] = make_uint4(cl.x, cl.y, cr.x, cr.y);
+        dst[5 * i + 1] = make_uint4(cl.z, cr.z, hl.z, hr.z);
+        dst[5 * i + 2] = make_uint4(hl.x, hl.y, hr.x, hr.y);
+        dst[5 * i + 3] = make_uint4(cl.w, cr.w, 0u, 0u);
+    }
+    } else {
     for (uint32_t i = threadIdx.x; i < 2 * sc.n_nodes; i += blockDim.x) dst[i + (i >> 2)] = __ldg(src + i); // 4 F4 per pair -> 5
+    }
     src = reinterpret_cast<const uint4 *>(sc.sph), dst = reinterpret_cast<uint4 *>(sph);
     for (uint32_t i = threadIdx.x; i < sc.n_slots; i += blockDim.x) dst[i] = __ldg(src + i);
     src = reinterpret_cast<const uint4 *>(sc.mats), dst = reinterpret_cast<uint4 *>(mats);
@@ -165,7 +185,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
     const uint32_t *chains = p.sc.chains, *sph_chain = p.sc.chains ? p.sc.sph_chain : nullptr, *quad_chain = p.sc.quad_chain;
     uint32_t *stack_mem = nullptr;
     if (SMEM) {
-        SmemScene s = stage_scene(p.sc, smem_raw);
+        SmemScene s = stage_scene<RT_PACKED(SMEM, QUADS)>(p.sc, smem_raw);
         nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta, stack_mem = s.stack;
         chains = s.chains, sph_chain = s.sph_chain, quad_chain = s.quad_chain;
     }
@@ -215,8 +235,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
             if (!alive && rank < avail) {
                 if (SPLIT) { // resume a path after its first segment
                     const uint32_t e = warp_next + rank;
+                    RT_DBG(e < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
                     const float4 qo = p.queue_o[e], qd = p.queue_d[e], qt = p.queue_t[e];
                     idx = __float_as_uint(qo.w);
+                    RT_DBG(idx < p.total_paths, RT_DBG_SAMPLE);
                     const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
                     rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
                     rng.block = __float_as_uint(qd.w) & 0x7fffffffu;
@@ -246,7 +268,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 
         // ---- one path segment: ray.go:32-54 unrolled front to back ----
         HitRec h;
-        trace_closest<Stack, COUNT, QUADS, SMEM, SMEM ? RT_SMEM_NODE_STRIDE : 32>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+        trace_closest<Stack, COUNT, QUADS, SMEM, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
                                                  chains, start);
         n_rays++;
         bool done;
@@ -258,13 +280,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
             V3 atten, emitted;
             bool scattered;
             if (QUADS && (h.slot & RT_HIT_QUAD)) {
+                RT_DBG((h.slot & ~RT_HIT_QUAD) < RT_DBG_B(n_quad_slots), RT_DBG_HIT_SLOT);
                 const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
                 const uint32_t mi = __float_as_uint(q[1].w);
+                RT_DBG(mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
                 const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
                 scattered = shade_hit_quad(m0, m1, p.sc.tex, q, h.t, rng, o, d, atten, emitted);
             } else {
+                RT_DBG(h.slot < RT_DBG_B(n_slots), RT_DBG_HIT_SLOT);
                 const F4 s = sph[h.slot];
                 const int mi = meta[h.slot].y;
+                RT_DBG((uint32_t)mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
                 const F4 m0 = mats[2 * mi], m1 = mats[2 * mi + 1];
                 scattered = shade_hit(m0, m1, p.sc.tex, s, h.t, rng, o, d, atten, emitted);
             }
@@ -279,6 +305,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
             }
         }
         if (done) {
+            RT_DBG(idx < p.total_paths && idx < RT_DBG_B(samples_cap), RT_DBG_SAMPLE);
             p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
             alive = false;
         }
@@ -315,7 +342,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
     Stack stack;
     const uint32_t *chains = p.sc.chains, *sph_chain = p.sc.chains ? p.sc.sph_chain : nullptr, *quad_chain = p.sc.quad_chain;
     if constexpr (SMEM) {
-        SmemScene s = stage_scene(p.sc, smem_raw);
+        SmemScene s = stage_scene<RT_PACKED(SMEM, QUADS)>(p.sc, smem_raw);
         nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta;
         chains = s.chains, sph_chain = s.sph_chain, quad_chain = s.quad_chain;
         stack.base = s.stack + threadIdx.x;
@@ -346,6 +373,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 rng.init(p.seed, pixel, p.sample_begin + k);
                 generate_ray(p.cam, rng, i, j, o, d);
             } else {
+                RT_DBG(item < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
                 const float4 qo = p.in_o[item], qd = p.in_d[item], qt = p.in_t[item];
                 idx = __float_as_uint(qo.w);
                 const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
@@ -359,7 +387,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 }
             }
             HitRec h;
-            trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+            trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
                                                FIRST ? nullptr : chains, start);
             n_rays++;
             hit_slot = h.slot;
@@ -370,12 +398,16 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 V3 atten, emitted;
                 bool scattered;
                 if (QUADS && (h.slot & RT_HIT_QUAD)) {
+                    RT_DBG((h.slot & ~RT_HIT_QUAD) < RT_DBG_B(n_quad_slots), RT_DBG_HIT_SLOT);
                     const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
                     const uint32_t mi = __float_as_uint(q[1].w);
+                    RT_DBG(mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
                     scattered = shade_hit_quad(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, q, h.t, rng, o, d, atten, emitted);
                 } else {
+                    RT_DBG(h.slot < RT_DBG_B(n_slots), RT_DBG_HIT_SLOT);
                     const F4 s = sph[h.slot];
                     const int mi = meta[h.slot].y;
+                    RT_DBG((uint32_t)mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
                     scattered = shade_hit(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, s, h.t, rng, o, d, atten, emitted);
                 }
                 rad = rad + thr * emitted; // ray.go:41,50
@@ -388,6 +420,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
             // no material of the reference both emits and scatters, so a survivor normally carries no
             // radiance; if one ever does, it is parked in the sample slot and flagged in the queue entry
             carries = survive && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f);
+            RT_DBG(idx < p.total_paths && idx < RT_DBG_B(samples_cap), RT_DBG_SAMPLE);
             if (!survive || carries) p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
         }
         // append survivors, consecutive entries for consecutive lanes
@@ -425,6 +458,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
         }
         if (survive) {
             const uint32_t e = first_entry + __popc(m & ((1u << lane) - 1u));
+            RT_DBG(e < p.total_paths && e < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
             p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
             p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block | (carries ? 0x80000000u : 0u)));
             p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(hit_slot)); // the primitive the survivor leaves
@@ -446,6 +480,8 @@ __global__ void reduce_kernel(const float4 *__restrict__ samples, float *__restr
                               uint32_t n_pixels, uint32_t spp_pass, int first_pass) {
     const uint32_t pp = blockIdx.x * blockDim.x + threadIdx.x;
     if (pp >= n_pixels) return;
+    RT_DBG((unsigned long long)pixel_begin + pp < RT_DBG_B(n_pixels), RT_DBG_PIXEL);
+    RT_DBG(((size_t)pp + 1) * spp_pass <= RT_DBG_B(samples_cap), RT_DBG_SAMPLE);
     float *a = accum + 3 * (size_t)(pixel_begin + pp);
     V3 sum = first_pass ? v3(0, 0, 0) : v3(a[0], a[1], a[2]);
     const float4 *s = samples + (size_t)pp * spp_pass;
@@ -479,7 +515,7 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ De
     typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
     Stack stack;
     if constexpr (SMEM) {
-        SmemScene s = stage_scene(sc, smem_raw);
+        SmemScene s = stage_scene<RT_PACKED(SMEM, QUADS)>(sc, smem_raw);
         nodes = s.nodes, sph = s.sph, quads = s.quads, meta = s.meta;
         stack.base = s.stack + threadIdx.x;
         stack.stride = BLOCK;
@@ -488,7 +524,7 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ De
         const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         HitRec h;
-        trace_closest<Stack, false, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, quads);
+        trace_closest<Stack, false, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, sc.root_ref, o, d, tmin, tmax, stack, h, nullptr, quads);
         if (h.slot == RT_REF_NONE) {
             id_out[i] = -1, t_out[i] = 0.0f;
         } else {

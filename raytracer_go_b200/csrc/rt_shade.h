@@ -139,6 +139,7 @@ RT_HD V3 image_texture(const DevImage &im, V3 oob, float u, float v) {
     float fj = v * (float)im.h;
     int i = (int)fi, j = (int)fj;
     if (i < 0 || i >= im.w || j < 0 || j >= im.h) return oob; // image.At outside Bounds()
+    RT_DBG((size_t)j * (size_t)im.w + (size_t)i < (size_t)im.w * (size_t)im.h, RT_DBG_TEXEL);
     const uint16_t *px = im.texels + ((size_t)j * (size_t)im.w + (size_t)i) * 4;
 #if defined(__CUDA_ARCH__)
     const ushort4 t = *reinterpret_cast<const ushort4 *>(px);
@@ -212,6 +213,8 @@ RT_HD V3 texture_value(const F4 &m0, const F4 &m1, uint32_t code, DevTex tex_, c
         if (((x + y + z) & 1) == 0) return v3(m0.x, m0.y, m0.z);
         return v3(m1.x, m1.y, m1.z);
     }
+    RT_DBG(tex != RT_TEX_NOISE || RT_CODE_IMG(code) < RT_DBG_B(n_perlins), RT_DBG_TEXTURE);
+    RT_DBG(tex != RT_TEX_IMAGE || RT_CODE_IMG(code) < RT_DBG_B(n_images), RT_DBG_TEXTURE);
     if (tex == RT_TEX_NOISE) return noise_texture(tex_.perlins[RT_CODE_IMG(code)], m0.w, point);
     if (tex == RT_TEX_IMAGE) {
         float u = hi.u, v = hi.v;

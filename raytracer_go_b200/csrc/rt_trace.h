@@ -21,6 +21,7 @@
 #ifndef RT_TRACE_H
 #define RT_TRACE_H
 
+#include "rt_debug.h"
 #include "rt_math.h"
 
 #if defined(__CUDACC__)
@@ -59,7 +60,10 @@ struct LocalStack {
     uint32_t e[N];
     int sp;
     RT_HD void reset() { sp = 0; }
-    RT_HD void push(uint32_t r) { e[sp++] = r; }
+    RT_HD void push(uint32_t r) {
+        RT_DBG(sp < N, RT_DBG_STACK);
+        e[sp++] = r;
+    }
     RT_HD uint32_t pop() { return sp > 0 ? e[--sp] : RT_REF_NONE; }
     RT_HD void push_if(bool c, uint32_t r) {
         if (c) push(r);
@@ -80,6 +84,7 @@ struct StridedStack {
     uint32_t base_s, top_s;
     __device__ __forceinline__ void reset() { base_s = top_s = (uint32_t)__cvta_generic_to_shared(base); }
     __device__ __forceinline__ void push(uint32_t r) {
+        RT_DBG(top_s - base_s < 4u * (uint32_t)stride * RT_DBG_B(stack_entries), RT_DBG_STACK);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(top_s), "r"(r));
         top_s += 4u * (uint32_t)stride;
     }
@@ -94,6 +99,7 @@ struct StridedStack {
     // "both children hit / one / none" almost every step, so branches there only add BSSY / BRA /
     // BSYNC around code that is executed anyway (control flow was 15 % of the issued instructions).
     __device__ __forceinline__ void push_if(bool c, uint32_t r) {
+        RT_DBG(!c || top_s - base_s < 4u * (uint32_t)stride * RT_DBG_B(stack_entries), RT_DBG_STACK);
         asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(top_s), "r"(r), "r"((uint32_t)c));
         top_s += c ? 4u * (uint32_t)stride : 0u;
     }
@@ -168,6 +174,32 @@ RT_HD bool box_test(const F4 &c, const F4 &h, V3 inv, V3 noi, V3 ainv, float tmi
     return tn <= tf;
 }
 
+#if defined(__CUDA_ARCH__)
+// The same slab test for BOTH children of a pair with sm_100's packed FP32 instructions (FFMA2: two fused
+// multiply-adds per lane and issue slot).  The shared-memory copy of a pair is stored transposed for it
+// (stage_scene in rt_kernels.cuh):
+//   w0 = (cL.x, cL.y, cR.x, cR.y)   w1 = (cL.z, cR.z, hL.z, hR.z)   w2 = (hL.x, hL.y, hR.x, hR.y)   w3 = (refL, refR, -, -)
+// so the x/y components of a box pair with the ray's (inv.x, inv.y) and the two z components with (inv.z, inv.z):
+// 9 FFMA2 instead of 18 FFMA per pair, the same fused operation per component, hence bit-identical results.
+// The kernels are bound by instruction issue, not by the FMA pipe (ncu: fma 33 %, issue 80 %).
+struct RayPairs {
+    float2 inv_xy, inv_zz, noi_xy, noi_zz, ainv_xy, ainv_zz;
+};
+__device__ __forceinline__ void box_test_pair(const F4 &w0, const F4 &w1, const F4 &w2, const RayPairs &r, float tmin,
+                                              float tbest, bool &hl, bool &hr, float &tl, float &tr) {
+    const float2 mL = __ffma2_rn(make_float2(w0.x, w0.y), r.inv_xy, r.noi_xy);
+    const float2 mR = __ffma2_rn(make_float2(w0.z, w0.w), r.inv_xy, r.noi_xy);
+    const float2 mZ = __ffma2_rn(make_float2(w1.x, w1.y), r.inv_zz, r.noi_zz);
+    const float2 nL = __ffma2_rn(make_float2(-w2.x, -w2.y), r.ainv_xy, mL), fL = __ffma2_rn(make_float2(w2.x, w2.y), r.ainv_xy, mL);
+    const float2 nR = __ffma2_rn(make_float2(-w2.z, -w2.w), r.ainv_xy, mR), fR = __ffma2_rn(make_float2(w2.z, w2.w), r.ainv_xy, mR);
+    const float2 nZ = __ffma2_rn(make_float2(-w1.z, -w1.w), r.ainv_zz, mZ), fZ = __ffma2_rn(make_float2(w1.z, w1.w), r.ainv_zz, mZ);
+    tl = rt_fmax(rt_fmax3(nL.x, nL.y, nZ.x), tmin);
+    tr = rt_fmax(rt_fmax3(nR.x, nR.y, nZ.y), tmin);
+    hl = tl <= rt_fmin(rt_fmin3(fL.x, fL.y, fZ.x), tbest);
+    hr = tr <= rt_fmin(rt_fmin3(fR.x, fR.y, fZ.y), tbest);
+}
+#endif
+
 // hittables.go:96-116 for one sphere, in the reference's operation order (unfused).
 // a = |d|^2 (hittables.go:98) is hoisted: it does not depend on the sphere.
 RT_HD bool sphere_candidate(const F4 &s, V3 o, V3 d, float a, float tmin, float &t_out) {
@@ -226,7 +258,8 @@ RT_HD int32_t slot_object_id(uint32_t slot, const I2 *__restrict__ meta, const F
 // pair of nodes then starts every 80 bytes, so the first 16-byte word of pair p lies in bank group 5p mod 8 —
 // all eight groups — instead of 4p mod 8 (two groups): the quarter-warp of an LDS.128 of 8 random nodes collides
 // far less (ncu r02e: 38 % of the shared wavefronts were conflict replays with the dense layout).
-template <class Stack, bool COUNT, bool QUADS = false, bool PRED = false, int NSTRIDE = 32>
+// PACKED: `nodes` is the transposed shared-memory copy (box_test_pair above); device code only.
+template <class Stack, bool COUNT, bool QUADS = false, bool PRED = false, int NSTRIDE = 32, bool PACKED = false>
 RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sph,
                          const I2 *__restrict__ meta, uint32_t root_ref, V3 o, V3 d, float tmin,
                          float tmax, Stack &stack, HitRec &hit, WorkCounters *wc,
@@ -236,6 +269,14 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
     const V3 noi = v3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
     const V3 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
     const float a = lensq(d);
+#if defined(__CUDA_ARCH__)
+    RayPairs rp;
+    if constexpr (PACKED) {
+        rp.inv_xy = make_float2(inv.x, inv.y), rp.inv_zz = make_float2(inv.z, inv.z);
+        rp.noi_xy = make_float2(noi.x, noi.y), rp.noi_zz = make_float2(noi.z, noi.z);
+        rp.ainv_xy = make_float2(ainv.x, ainv.y), rp.ainv_zz = make_float2(ainv.z, ainv.z);
+    }
+#endif
     float tbest = tmax;
     uint32_t best_slot = RT_REF_NONE;
     int32_t best_id = 0x7fffffff;
@@ -243,7 +284,9 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
     stack.reset();
     uint32_t ref = root_ref;
     if (chains != nullptr && start != RT_REF_NONE) {
+        RT_DBG(start < RT_DBG_B(n_chain_words), RT_DBG_CHAIN);
         const uint32_t len = chains[start];
+        RT_DBG(start + len + 1 < RT_DBG_B(n_chain_words), RT_DBG_CHAIN);
         for (uint32_t k = 1; k <= len; k++) stack.push(chains[start + k]);
         ref = chains[start + len + 1];
     }
@@ -251,14 +294,27 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
         // "while-while": every lane first descends through inner nodes until it holds a leaf (or
         // nothing), then the lanes test their leaves together.  RT_REF_NONE has the leaf bit set.
         while (!(ref & RT_LEAF)) {
+            RT_DBG(!(ref & 1u) && ref + 1 < RT_DBG_B(n_nodes), RT_DBG_NODE);
             const F4 *np = reinterpret_cast<const F4 *>(reinterpret_cast<const char *>(nodes) + (size_t)ref * NSTRIDE);
-            const F4 l0 = np[0], l1 = np[1];
-            const F4 r0 = np[2], r1 = np[3]; // (the sibling follows its node directly for either stride)
             float tl, tr;
-            const bool hl = box_test(l0, l1, inv, noi, ainv, tmin, tbest, tl);
-            const bool hr = box_test(r0, r1, inv, noi, ainv, tmin, tbest, tr);
+            bool hl, hr;
+            uint32_t lref, rref;
+#if defined(__CUDA_ARCH__)
+            if constexpr (PACKED) {
+                const F4 w0 = np[0], w1 = np[1], w2 = np[2];
+                const uint2 refs = *reinterpret_cast<const uint2 *>(np + 3);
+                box_test_pair(w0, w1, w2, rp, tmin, tbest, hl, hr, tl, tr);
+                lref = refs.x, rref = refs.y;
+            } else
+#endif
+            {
+                const F4 l0 = np[0], l1 = np[1];
+                const F4 r0 = np[2], r1 = np[3]; // (the sibling follows its node directly for either stride)
+                hl = box_test(l0, l1, inv, noi, ainv, tmin, tbest, tl);
+                hr = box_test(r0, r1, inv, noi, ainv, tmin, tbest, tr);
+                lref = as_uint(l0.w), rref = as_uint(r0.w);
+            }
             if (COUNT) wc->box_tests += 2;
-            const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
             // nearer child first, the other one (if hit) on the stack; nothing hit: pop
             if (PRED) {
                 const bool take_l = hl && (tl <= tr || !hr);
@@ -278,6 +334,7 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
         }
         if (ref == RT_REF_NONE) break;
         const uint32_t first = (ref & RT_LEAF_SLOT_MASK) >> 3, count = (ref & 7u) + 1;
+        RT_DBG(first + count <= ((ref & RT_LEAF_QUAD) ? RT_DBG_B(n_quad_slots) : RT_DBG_B(n_slots)), RT_DBG_LEAF);
         if (QUADS && (ref & RT_LEAF_QUAD)) {
             for (uint32_t s = first; s < first + count; s++) {
                 float t;

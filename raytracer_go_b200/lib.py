@@ -5,7 +5,10 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librt_b200.so")
+# RT_B200_DEBUG=1: the bounds-checked build of the same sources (csrc/rt_debug.h, `make librt_b200_debug.so`).
+# RT_B200_LIBRARY: another build of the same library (csrc/Makefile `variant`), for A/B measurements.
+_DEFAULT = "librt_b200_debug.so" if os.environ.get("RT_B200_DEBUG", "0") not in ("", "0") else "librt_b200.so"
+LIB_PATH = os.environ.get("RT_B200_LIBRARY") or os.path.join(_HERE, "csrc", _DEFAULT)
 
 _lib = None
 

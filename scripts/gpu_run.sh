@@ -12,6 +12,7 @@
 #   reference       bench.py --impl reference --steps 2 --warmup 1
 #   configs         bench.py on C1 C3 C4 C5(64 spp) CB, short
 #   sweep:VAR:a,b,c bench-short once per value of environment variable VAR
+#   ab:NAME[:cfgs]  the default library against the variant build csrc/librt_b200_NAME.so
 #   ncu-launches    per-launch durations of the bench command (gpu__time_duration.sum)
 #   ncu-full[:SPP]  ncu --set full of one primary + one secondary launch at SPP (default 82) spp
 #   scale           bench.py at N = 1/2/4/8 under torchrun as the driver launches it, weak + strong
@@ -65,6 +66,13 @@ for step in "$@"; do
       for v in $vals; do for cfg in $cfgs; do
         env $var=$v timeout 600 python bench.py --config $cfg --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-strong > gpurun_out/${TAG}_sweep_${var}_${v}_${cfg}.json 2>> gpurun_out/${TAG}_sweep.err
         line "$var=$v" gpurun_out/${TAG}_sweep_${var}_${v}_${cfg}.json
+      done; done ;;
+    ab:*)  # ab:NAME[:cfgs] — the default library against csrc/librt_b200_NAME.so (csrc/Makefile `variant`)
+      name=$(echo "$step" | cut -d: -f2); cfgs=$(echo "$step" | cut -s -d: -f3 | tr ',' ' '); [ -z "$cfgs" ] && cfgs="C2"
+      for cfg in $cfgs; do for which in default $name; do
+        libenv=""; [ $which != default ] && libenv="RT_B200_LIBRARY=raytracer_go_b200/csrc/librt_b200_${which}.so"
+        env $libenv timeout 600 python bench.py --config $cfg --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-strong > gpurun_out/${TAG}_ab_${which}_${cfg}.json 2>> gpurun_out/${TAG}_ab.err
+        line "lib=$which" gpurun_out/${TAG}_ab_${which}_${cfg}.json
       done; done ;;
     ncu-launches)
       CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-strong"

@@ -3,6 +3,8 @@
 Full-size runs are compared with the oracle where the oracle finishes in seconds (low spp), and
 otherwise through size-independent properties: sample-split additivity, determinism, statistics.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,10 @@ from raytracer_go_b200 import api, scenes
 
 pytestmark = pytest.mark.gpu
 SEED = scenes.RENDER_SEED
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# device-vs-World.Hit ID mismatch bounds beyond the 150-unit envelope of the 1 M-sphere scene, per distance band:
+# 2x the rate measured on the GPU (profiles/r02j_c4_parity_by_distance.txt, FAR camera)
+C4_FAR_BOUNDS = [(150, 200, 0.02), (200, 300, 0.05), (300, 500, 0.10), (500, 1000, 0.20), (1000, np.inf, 0.30)]
 
 
 def _psnr(a, b, peak):
@@ -65,6 +71,41 @@ def test_c3_earth_plus_random_full_size(gpu, orc):
     assert (ids == len(scene.spheres) - 1).mean() > 0.005
 
 
+def test_c5_4k_frame_equals_oracle(gpu, orc, random_scene):
+    """Config C5's frame (3840x2160, 8.3 M pixels) at 1 spp against the oracle (World.Hit list, iterative radiance
+    order): bit-identical FP32 sums and RGB8, the same number of rays."""
+    cam = api.camera_from_options(scenes.camera_options(3840, 1))
+    assert (cam.width, cam.height) == (3840, 2160)
+    with api.Scene(random_scene) as sc:
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    rrgb, racc, rst = orc.render(random_scene, cam, SEED, order=orc.ORDER_ITERATIVE)
+    same = (acc.view(np.uint32) == racc.view(np.uint32)).all(-1)
+    assert same.mean() > 0.99999, f"{(~same).sum()} of {same.size} pixel sums differ"   # libm last-bit cases only
+    assert (rgb != rrgb).any(-1).sum() <= 16
+    assert abs(int(st.rays) - int(rst.rays)) <= 256 and st.samples == 3840 * 2160
+
+
+def test_c2_named_size_converged_psnr(gpu):
+    """north_star at the NAMED size: config C2's 1200x675 frame at 4096 spp, depth 50, on the device (seed 0xA11CE)
+    against the committed frame of the oracle running the reference's algorithm (random-axis BVH, recursive radiance)
+    on its own samples (seed 0xB0B; tests/golden/make_c2_converged.py, ~5 min of 16 cores).  PSNR >= 40 dB on the
+    linear means and on RGB8; stated per-pixel tolerance |difference of means| <= 0.06; no bias."""
+    g = np.load(os.path.join(GOLDEN, "c2_4096spp_reference_algorithm_u16.npz"))
+    scene = scenes.random_scene()
+    assert str(g["scene_sha"]) == scene.sha256() and int(g["spp"]) == 4096
+    cam = api.camera_from_options(scenes.camera_options(1200, 4096))
+    with api.Scene(scene) as sc:
+        rgb, acc, st = sc.render(cam, 0xA11CE, want_accum=True)
+    assert st.samples == 1200 * 675 * 4096
+    mean = np.clip(acc / 4096, 0, 1)
+    rmean = g["mean_u16"].astype(np.float32) / 65535.0
+    assert mean.shape == rmean.shape == (675, 1200, 3)
+    assert _psnr(mean, rmean, 1.0) >= 40.0
+    assert _psnr(rgb, g["rgb"], 255.0) >= 40.0
+    assert np.abs(mean - rmean).max() <= 0.06
+    assert abs(float(mean.mean()) - float(rmean.mean())) < 5e-4
+
+
 def test_c5_4k_sample_split_additivity(gpu, random_scene):
     """Config C5 frame (3840x2160): samples [0,2) == [0,1) + [1,2), and the run is deterministic."""
     cam = api.camera_from_options(scenes.camera_options(3840, 2))
@@ -77,34 +118,59 @@ def test_c5_4k_sample_split_additivity(gpu, random_scene):
     assert np.array_equal((a0 + a1).view(np.uint32), a01.view(np.uint32))  # two terms: one rounding, same order
 
 
-def test_c4_million_spheres(gpu, orc):
-    """Config C4: ~1e6 spheres (global-memory BVH, local-memory stack).  Closest hits against the
-    oracle's brute-force list on a ray subset, against its BVH on a larger set."""
-    scene, o = scenes.build_config("C4", spp=1)
-    assert len(scene.spheres) > 990_000
-    cam = api.camera_from_options(o)
+def test_c4_million_spheres_full_primary_frame(gpu, orc):
+    """Config C4: ~1e6 spheres (global-memory BVH, local-memory stack).  north_star: primary-ray closest-hit IDs
+    bit-exact on an identical ray set.  ALL 2 073 600 primary rays of the 1920x1080 frame are traced on the device and
+    compared with (1) the brute-force World.Hit (hittables.go:55-72, the ground truth) on 60 000 seeded rays — IDs and
+    the bits of t — and (2) the reference's own BVH.Hit (bvh.go:220-249) on the whole frame; where those two differ the
+    list decides.  Every primary hit of this camera lies 25..125 units away, inside the scene's 150-unit envelope
+    (DESIGN.md section 3); the mismatch rates by distance are committed as profiles/r02*_c4_parity_by_distance.txt."""
+    from tests import parity_report
+    r = parity_report.run("C4")
+    scene, cam, sub = r["scene"], r["cam"], r["sub"]
+    assert len(scene.spheres) > 990_000 and (cam.width, cam.height) == (1920, 1080)
+    ids, ts, lids, lts = r["ids"], r["ts"], r["lids"], r["lts"]
+    dist = lts * r["dnorm"][sub]
+    assert (lids >= 0).all() and float(dist.max()) < 150.0          # the whole frame is inside the envelope
+    assert np.array_equal(ids[sub], lids)                            # 60 000 rays: IDs exact
+    assert np.array_equal(ts[sub].view(np.uint32), lts.view(np.uint32))   # ... and every bit of t
+    # the full frame against the reference's BVH.Hit; its own grazing misses (bvh.go:52-102 culls with the unpadded
+    # box) are settled by the list
+    diff = np.flatnonzero(ids != r["bids"])
+    assert len(diff) <= 20, f"{len(diff)} of {len(ids)} rays differ from BVH.Hit"
+    if len(diff):
+        wids, wts = orc.trace(scene, r["ro"][diff], r["rd"][diff], mode=orc.MODE_LINEAR)
+        assert np.array_equal(ids[diff], wids) and np.array_equal(ts[diff].view(np.uint32), wts.view(np.uint32))
+    same = ids == r["bids"]
+    assert np.array_equal(ts[same].view(np.uint32), r["bts"][same].view(np.uint32))
     with api.Scene(scene) as sc:
         info = sc.bvh_info()
         assert info.in_shared_memory == 0 and info.max_depth < 60
-        n_pix = cam.width * cam.height
-        rng = np.random.default_rng(1)
-        pix = np.sort(rng.choice(n_pix, 60_000, replace=False))
-        ro = np.empty((len(pix), 3), np.float32)
-        rd = np.empty((len(pix), 3), np.float32)
-        for k, p in enumerate(pix[:3000]):
-            ro[k], rd[k] = (x[0] for x in orc.primary_rays(cam, SEED, int(p), 1, 0, 1))
-        ids, ts = sc.trace(ro[:3000], rd[:3000])
-        rids, rts = orc.trace(scene, ro[:3000], rd[:3000], mode=orc.MODE_LINEAR)
-        # beyond ~150 units the reference's float32 discriminant is noise for r = 0.2 (DESIGN.md §3);
-        # inside that envelope the answer must be the list's, bit for bit
-        near = (rids < 0) | (rts * np.linalg.norm(rd[:3000], axis=1) < 150)
-        assert np.array_equal(ids[near], rids[near])
-        hit = near & (rids >= 0)
-        assert np.array_equal(ts[hit].view(np.uint32), rts[hit].view(np.uint32))
-        assert (ids != rids).mean() < 0.02
         rgb, acc, st = sc.render(cam, SEED, want_accum=True)
-    assert st.samples == n_pix and st.rays > st.samples and np.isfinite(acc).all()
+    assert st.samples == cam.width * cam.height and st.rays > st.samples and np.isfinite(acc).all()
     assert rgb.std() > 5  # an actual picture, not a constant
+
+
+def test_c4_far_camera_envelope(gpu, orc):
+    """The same scene seen from low above the ground across the grid (hits out to ~1000 units): inside the 150-unit
+    envelope the device equals World.Hit bit for bit; beyond it a 0.2-radius sphere is below the resolution of the
+    reference's float32 discriminant (r^2 = 0.04 against ulp(|o-c|^2) >= 0.004 at 200 units) and the reference's own
+    BVH.Hit disagrees with its World.Hit there too — the device's rate must stay within the measured one
+    (profiles/r02*_c4_parity_by_distance.txt, second table) and is asserted per distance band."""
+    from tests import parity_report
+    r = parity_report.run("C4", n_linear=20_000, far=True, full_bvh=False)
+    sub, ids, ts, lids, lts = r["sub"], r["ids"][r["sub"]], r["ts"][r["sub"]], r["lids"], r["lts"]
+    dist = np.where(lids >= 0, lts * r["dnorm"][sub], 0.0)
+    near = dist < 150.0
+    assert near.sum() > 2000 and (~near).sum() > 2000              # the camera does reach beyond the envelope
+    assert np.array_equal(ids[near], lids[near])
+    hit = near & (lids >= 0)
+    assert np.array_equal(ts[hit].view(np.uint32), lts[hit].view(np.uint32))
+    for lo, hi, bound in C4_FAR_BOUNDS:
+        m = (dist >= lo) & (dist < hi)
+        if m.sum() >= 200:
+            rate = float((ids[m] != lids[m]).mean())
+            assert rate <= bound, f"[{lo}, {hi}): {rate:.3%} ID mismatches > {bound:.3%}"
 
 
 def test_c2_full_size_500spp_properties(gpu, orc, random_scene):
