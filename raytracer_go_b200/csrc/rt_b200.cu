@@ -84,6 +84,8 @@ struct Workspace {
     size_t h_accum_cap = 0; // floats (pinned)
     float4 *queue = nullptr; // staged mode: 2 (ping-pong) x 3 x capacity float4 (origin, direction, throughput)
     size_t queue_cap = 0;    // elements in total
+    unsigned char *gather = nullptr; // rt_render_multi: tile-split image (+ sums) assembled on the root / sample-split receive buffer
+    size_t gather_cap = 0;           // bytes
 };
 static Workspace g_ws[RT_MAX_DEVICES];
 
@@ -115,9 +117,9 @@ extern "C" void rt_workspace_release(int device) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         cudaGetLastError();
-        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue) continue;
-        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb), cudaFree(w.queue);
-        w.queue = nullptr, w.queue_cap = 0;
+        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue && !w.gather) continue;
+        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb), cudaFree(w.queue), cudaFree(w.gather);
+        w.queue = nullptr, w.queue_cap = 0, w.gather = nullptr, w.gather_cap = 0;
         if (w.h_rgb) cudaFreeHost(w.h_rgb);
         if (w.h_accum) cudaFreeHost(w.h_accum);
         w.samples = nullptr, w.accum = nullptr, w.rgb = nullptr, w.h_rgb = nullptr, w.h_accum = nullptr;
@@ -965,6 +967,27 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *camera, const rt_rend
 //  * tile-split (RT_FLAG_TILE_SPLIT): device k renders scanlines k, k+n, k+2n, ... at all samples
 //    and resolves them itself; the host interleaves the rows.  No exchange between devices, and the
 //    image is bit-identical to the single-GPU render.
+// Direct peer access between every pair of the call's devices (NVLink / NVSwitch on a B200 box): peer copies then move
+// device to device without staging.  Done once per pair and process; a pair that cannot be peers still works — the
+// runtime stages those copies.
+static void enable_peer_access(const std::vector<int> &devs) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, bool> done;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int a : devs)
+        for (int b : devs) {
+            if (a == b || done.count(std::make_pair(a, b))) continue;
+            done[std::make_pair(a, b)] = true;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) {
+                cudaGetLastError();
+                continue;
+            }
+            if (cudaSetDevice(a) == cudaSuccess) cudaDeviceEnablePeerAccess(b, 0);
+            cudaGetLastError(); // cudaErrorPeerAccessAlreadyEnabled is fine
+        }
+}
+
 static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *camera, const rt_render_opts *opts,
                                const int32_t *devices, int32_t n_devices, uint8_t *rgb_out, float *accum_out,
                                rt_stats *stats) {
@@ -1014,6 +1037,36 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
     HostSceneParts parts;
     rc = host_scene_parts(desc, &parts);
     if (rc != RT_OK) return rc;
+    const bool timing = getenv("RT_B200_MULTI_TIMING") != nullptr; // host-side phases of the call, to stderr
+    double t_lap = t0;
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const double t1 = now_ms();
+        fprintf(stderr, "[multi] %-24s %7.2f ms\n", what, t1 - t_lap);
+        t_lap = t1;
+    };
+    lap("validate + BVH build");
+    // the root's buffers every device writes into or reads from, allocated before the device threads start
+    const int root = devs[0];
+    Workspace &w0 = g_ws[root];
+    RC(select_device(root));
+    enable_peer_access(devs);
+    RC(ws_reserve(w0.rgb, w0.rgb_cap, (size_t)n_pix * 3));
+    RC(ws_reserve(w0.h_rgb, w0.h_rgb_cap, (size_t)n_pix * 3, true));
+    if (accum_out) RC(ws_reserve(w0.h_accum, w0.h_accum_cap, n_acc, true));
+    unsigned char *root_rgb = nullptr;
+    float *root_acc = nullptr;
+    if (tiles) { // [sums (optional) | image]
+        RC(ws_reserve(w0.gather, w0.gather_cap, (accum_out ? n_acc * sizeof(float) : 0) + (size_t)n_pix * 3));
+        root_acc = reinterpret_cast<float *>(w0.gather);
+        root_rgb = w0.gather + (accum_out ? n_acc * sizeof(float) : 0);
+    } else {
+        for (int k = 0; k < n_devices; k++) { // receive buffers of the reduction tree
+            if (select_device(devs[k]) != RT_OK) continue; // reported by the device's thread
+            RC(ws_reserve(g_ws[devs[k]].gather, g_ws[devs[k]].gather_cap, n_acc * sizeof(float)));
+        }
+    }
+    lap("peer access + buffers");
     // a device thread that cannot be started joins the ones that were before the error is reported
     struct Joiner {
         std::vector<std::thread> v;
@@ -1050,8 +1103,6 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
                 const size_t my_acc = (size_t)jj.o.row_count * row_bytes;
                 jj.rc = ws_reserve(ws.accum, ws.accum_cap, my_acc);
                 if (jj.rc == RT_OK && tiles) jj.rc = ws_reserve(ws.rgb, ws.rgb_cap, my_acc);
-                if (jj.rc == RT_OK && tiles) jj.rc = ws_reserve(ws.h_rgb, ws.h_rgb_cap, my_acc, true);
-                if (jj.rc == RT_OK && tiles && accum_out) jj.rc = ws_reserve(ws.h_accum, ws.h_accum_cap, my_acc, true);
                 uint32_t launches = 0;
                 cudaStream_t st = jj.scene->stream;
                 if (jj.rc == RT_OK) jj.rc = scene_events(jj.scene, 2);
@@ -1060,15 +1111,21 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
                 if (jj.rc == RT_OK) {
                     cudaError_t e = cudaSuccess;
                     if (tiles) {
+                        // resolve the device's own rows, then put them where they belong in the root's image: local
+                        // row r is row k + r*n of the caller's row set — one strided peer copy over NVLink
                         const uint32_t my_pix = (uint32_t)(my_acc / 3);
                         resolve_kernel<<<(my_pix + 255) / 256, 256, 0, st>>>(ws.accum, ws.rgb, my_pix, 1.0f / (float)spp);
                         launches++;
                         e = cudaGetLastError();
+                        if (e == cudaSuccess)
+                            e = cudaMemcpy2DAsync(root_rgb + (size_t)k * row_bytes, (size_t)n_devices * row_bytes, ws.rgb, row_bytes,
+                                                  row_bytes, (size_t)jj.o.row_count, cudaMemcpyDefault, st);
+                        if (e == cudaSuccess && accum_out)
+                            e = cudaMemcpy2DAsync(root_acc + (size_t)k * row_bytes, (size_t)n_devices * row_bytes * sizeof(float), ws.accum,
+                                                  row_bytes * sizeof(float), row_bytes * sizeof(float), (size_t)jj.o.row_count,
+                                                  cudaMemcpyDefault, st);
                     }
                     if (e == cudaSuccess) e = cudaEventRecord(jj.scene->events[1], st);
-                    if (e == cudaSuccess && tiles) e = cudaMemcpyAsync(ws.h_rgb, ws.rgb, my_acc, cudaMemcpyDeviceToHost, st);
-                    if (e == cudaSuccess && tiles && accum_out)
-                        e = cudaMemcpyAsync(ws.h_accum, ws.accum, my_acc * sizeof(float), cudaMemcpyDeviceToHost, st);
                     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
                     if (e != cudaSuccess) jj.rc = fail(RT_ERR_CUDA, "render failed on device %d: %s", devs[k], cudaGetErrorString(e));
                     else cudaEventElapsedTime(&jj.st.ms_render, jj.scene->events[0], jj.scene->events[1]);
@@ -1079,6 +1136,7 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
         });
     }
     for (auto &t : threads) t.join();
+    lap("render (all devices)");
     auto cleanup = [&]() {
         for (auto &j : jobs)
             if (j.scene) free_scene(j.scene);
@@ -1091,49 +1149,62 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
             return fail(code, "%s", msg.c_str());
         }
 
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = cudaSetDevice(root);
+    cudaStream_t st0 = jobs[0].scene->stream;
     if (tiles) {
-        // row r of the caller's row set was rendered by device r % n as its local row r / n
-        for (int r = 0; r < rows.count; r++) {
-            const Workspace &w = g_ws[devs[r % n_devices]];
-            const size_t local = (size_t)(r / n_devices) * row_bytes;
-            memcpy(rgb_out + (size_t)r * row_bytes, w.h_rgb + local, row_bytes);
-            if (accum_out) memcpy(accum_out + (size_t)r * row_bytes, w.h_accum + local, row_bytes * sizeof(float));
+        // every device has put its rows into the root's buffers (peer copies above): one read-back
+        if (e == cudaSuccess) e = cudaMemcpyAsync(w0.h_rgb, root_rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st0);
+        if (e == cudaSuccess && accum_out) e = cudaMemcpyAsync(w0.h_accum, root_acc, n_acc * sizeof(float), cudaMemcpyDeviceToHost, st0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+        if (e == cudaSuccess) {
+            memcpy(rgb_out, w0.h_rgb, (size_t)n_pix * 3);
+            if (accum_out) memcpy(accum_out, w0.h_accum, n_acc * sizeof(float));
         }
     } else {
-        // gather on devices[0]: peer copy + add, in device order
-        const int root = devs[0];
-        Workspace &w0 = g_ws[root];
-        e = cudaSetDevice(root);
-        float *tmp = nullptr;
-        if (e == cudaSuccess && n_devices > 1) e = cudaMalloc(&tmp, n_acc * sizeof(float));
-        cudaStream_t st0 = jobs[0].scene->stream;
-        for (int k = 1; k < n_devices && e == cudaSuccess; k++) {
-            if (jobs[k].idle) continue;
-            e = cudaMemcpyPeerAsync(tmp, root, g_ws[devs[k]].accum, devs[k], n_acc * sizeof(float), st0);
-            if (e == cudaSuccess) {
-                add_kernel<<<(unsigned)((n_acc + 255) / 256), 256, 0, st0>>>(w0.accum, tmp, n_acc);
-                e = cudaGetLastError();
-            }
+        // Sum of the devices' accumulators on devices[0] by a binary tree: in round s device k (k a multiple of 2s)
+        // receives the partial sum of device k+s by a peer copy over NVLink into its gather buffer and adds it —
+        // log2(n) rounds, the copies of one round in flight together, instead of n-1 copies and adds queued one
+        // after the other on the root.  The tree is fixed by n, so the result is deterministic.
+        std::vector<int> active;
+        for (int k = 0; k < n_devices; k++)
+            if (!jobs[k].idle) active.push_back(k);
+        std::vector<cudaEvent_t> done(active.size(), nullptr);
+        for (size_t a = 0; a < active.size() && e == cudaSuccess; a++) {
+            e = cudaSetDevice(devs[active[a]]);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[a], cudaEventDisableTiming);
         }
-        if (e == cudaSuccess) {
-            rc = ws_reserve(w0.rgb, w0.rgb_cap, (size_t)n_pix * 3);
-            if (rc == RT_OK) rc = ws_reserve(w0.h_rgb, w0.h_rgb_cap, (size_t)n_pix * 3, true);
-            if (rc == RT_OK && accum_out) rc = ws_reserve(w0.h_accum, w0.h_accum_cap, n_acc, true);
-            if (rc == RT_OK) {
-                resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st0>>>(w0.accum, w0.rgb, n_pix, 1.0f / (float)spp);
-                e = cudaGetLastError();
-                if (e == cudaSuccess) e = cudaMemcpyAsync(w0.h_rgb, w0.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st0);
-                if (e == cudaSuccess && accum_out) e = cudaMemcpyAsync(w0.h_accum, w0.accum, n_acc * sizeof(float), cudaMemcpyDeviceToHost, st0);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+        for (size_t step = 1; step < active.size() && e == cudaSuccess; step *= 2)
+            for (size_t a = 0; a + step < active.size() && e == cudaSuccess; a += 2 * step) {
+                const int kr = active[a], ks = active[a + step];
+                Workspace &wr = g_ws[devs[kr]];
+                cudaStream_t sr = jobs[kr].scene->stream, ss = jobs[ks].scene->stream;
+                e = cudaSetDevice(devs[ks]);
+                if (e == cudaSuccess) e = cudaEventRecord(done[a + step], ss); // the sender's partial sum is complete
+                if (e == cudaSuccess) e = cudaSetDevice(devs[kr]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(sr, done[a + step], 0);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyPeerAsync(wr.gather, devs[kr], g_ws[devs[ks]].accum, devs[ks], n_acc * sizeof(float), sr);
                 if (e == cudaSuccess) {
-                    memcpy(rgb_out, w0.h_rgb, (size_t)n_pix * 3);
-                    if (accum_out) memcpy(accum_out, w0.h_accum, n_acc * sizeof(float));
+                    add_kernel<<<(unsigned)((n_acc + 255) / 256), 256, 0, sr>>>(wr.accum, reinterpret_cast<const float *>(wr.gather), n_acc);
+                    e = cudaGetLastError();
                 }
             }
+        if (e == cudaSuccess) e = cudaSetDevice(root);
+        if (e == cudaSuccess) {
+            resolve_kernel<<<(n_pix + 255) / 256, 256, 0, st0>>>(w0.accum, w0.rgb, n_pix, 1.0f / (float)spp);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w0.h_rgb, w0.rgb, (size_t)n_pix * 3, cudaMemcpyDeviceToHost, st0);
+            if (e == cudaSuccess && accum_out) e = cudaMemcpyAsync(w0.h_accum, w0.accum, n_acc * sizeof(float), cudaMemcpyDeviceToHost, st0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st0);
+            if (e == cudaSuccess) {
+                memcpy(rgb_out, w0.h_rgb, (size_t)n_pix * 3);
+                if (accum_out) memcpy(accum_out, w0.h_accum, n_acc * sizeof(float));
+            }
         }
-        if (tmp) cudaFree(tmp);
+        for (auto ev : done)
+            if (ev) cudaEventDestroy(ev);
     }
+    lap("exchange + read-back");
     if (stats) {
         memset(stats, 0, sizeof *stats);
         for (auto &j : jobs) {
@@ -1147,8 +1218,9 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
         stats->ms_total = (float)(now_ms() - t0);
     }
     cleanup();
+    lap("destroy scenes");
     if (rc != RT_OK) return rc;
-    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "multi-device gather failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "multi-device exchange failed: %s", cudaGetErrorString(e));
     return RT_OK;
 }
 

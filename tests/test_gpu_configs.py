@@ -13,9 +13,10 @@ from raytracer_go_b200 import api, scenes
 pytestmark = pytest.mark.gpu
 SEED = scenes.RENDER_SEED
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-# device-vs-World.Hit ID mismatch bounds beyond the 150-unit envelope of the 1 M-sphere scene, per distance band:
-# 2x the rate measured on the GPU (profiles/r02j_c4_parity_by_distance.txt, FAR camera)
-C4_FAR_BOUNDS = [(150, 200, 0.02), (200, 300, 0.05), (300, 500, 0.10), (500, 1000, 0.20), (1000, np.inf, 0.30)]
+# device-vs-World.Hit ID mismatch bounds beyond the 150-unit envelope of the 1 M-sphere scene, per distance band: about
+# twice the rate measured on the GPU (profiles/r02j_c4_parity_by_distance.txt, FAR camera: 0 / 0 / 3.65 % / 10.5 %; the
+# reference's own BVH.Hit against its World.Hit on the same rays: 0.9 % / 8.5 % / 46 % / 68 %)
+C4_FAR_BOUNDS = [(150, 200, 0.01), (200, 300, 0.01), (300, 500, 0.08), (500, 1000, 0.25), (1000, np.inf, 0.40)]
 
 
 def _psnr(a, b, peak):
@@ -158,17 +159,17 @@ def test_c4_far_camera_envelope(gpu, orc):
     BVH.Hit disagrees with its World.Hit there too — the device's rate must stay within the measured one
     (profiles/r02*_c4_parity_by_distance.txt, second table) and is asserted per distance band."""
     from tests import parity_report
-    r = parity_report.run("C4", n_linear=20_000, far=True, full_bvh=False)
+    r = parity_report.run("C4", n_linear=40_000, far=True, full_bvh=False)
     sub, ids, ts, lids, lts = r["sub"], r["ids"][r["sub"]], r["ts"][r["sub"]], r["lids"], r["lts"]
     dist = np.where(lids >= 0, lts * r["dnorm"][sub], 0.0)
     near = dist < 150.0
-    assert near.sum() > 2000 and (~near).sum() > 2000              # the camera does reach beyond the envelope
+    assert near.sum() > 2000 and (~near).sum() > 1000              # the camera does reach beyond the envelope
     assert np.array_equal(ids[near], lids[near])
     hit = near & (lids >= 0)
     assert np.array_equal(ts[hit].view(np.uint32), lts[hit].view(np.uint32))
     for lo, hi, bound in C4_FAR_BOUNDS:
         m = (dist >= lo) & (dist < hi)
-        if m.sum() >= 200:
+        if m.sum() >= 150:
             rate = float((ids[m] != lids[m]).mean())
             assert rate <= bound, f"[{lo}, {hi}): {rate:.3%} ID mismatches > {bound:.3%}"
 
