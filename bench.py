@@ -370,8 +370,9 @@ def main():
     # ---- algorithmic work per sample, counted by the instrumented kernels on the same workload at a
     # reduced spp (per-ray statistics do not depend on spp).  The roofline's numerator is the work of the plain
     # top-down traversal of the binary tree — round 1's definition, 1 755 lane-instr/sample on C2 — counted on a
-    # scene handle built WITHOUT the leaf-start chains; what today's kernels execute (fewer box tests: leaf start
-    # skips the ancestors of the leaf a ray leaves) is reported next to it as `executed`. ----
+    # scene handle built WITHOUT the leaf-start chains and rendered WITHOUT the per-pixel candidate lists; what today's
+    # kernels execute (fewer box tests: leaf start skips the ancestors of the leaf a ray leaves, camera rays test their
+    # pixel's candidate list instead of walking the tree) is reported next to it as `executed`. ----
     cnt_spp = max(1, min(spp, 4))
 
     def count_work(scene_handle):
@@ -383,15 +384,17 @@ def main():
                 "segments_per_sample": seg, "box_tests_per_ray": n_box, "sphere_tests_per_ray": n_sph, "hit_fraction": n_hit,
                 "bytes_per_ray": n_box * B_BOX + n_sph * B_SPH + n_hit * B_HIT}
     executed = count_work(sc)
-    prev = os.environ.get("RT_B200_LEAF_START")
-    os.environ["RT_B200_LEAF_START"] = "0"
+    # the reference algorithm's work: every ray traverses the tree top-down — no leaf start, no per-pixel candidate lists
+    saved = {k: os.environ.get(k) for k in ("RT_B200_LEAF_START", "RT_B200_PIXEL_LISTS")}
+    os.environ["RT_B200_LEAF_START"] = os.environ["RT_B200_PIXEL_LISTS"] = "0"
     with api.Scene(scene_data, local_rank) as sc_ref:
         sc_ref.set_stream(stream.cuda_stream)
         algo = count_work(sc_ref)
-    if prev is None:
-        del os.environ["RT_B200_LEAF_START"]
-    else:
-        os.environ["RT_B200_LEAF_START"] = prev
+    for k, v in saved.items():
+        if v is None:
+            del os.environ[k]
+        else:
+            os.environ[k] = v
     instr_per_sample, seg = algo["instr_per_sample"], algo["segments_per_sample"]
     bytes_per_ray = algo["bytes_per_ray"]
     peaks, peak_src = measured_peaks()
@@ -419,7 +422,8 @@ def main():
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz {peaks['sm_max_mhz']:.0f} ({peak_src} MEASURED_PEAKS.json clock)",
         "instr_per_sample": instr_per_sample, "segments_per_sample": seg, "box_tests_per_ray": algo["box_tests_per_ray"],
         "sphere_tests_per_ray": algo["sphere_tests_per_ray"], "hit_fraction": algo["hit_fraction"], "counted_at_spp": cnt_spp,
-        "numerator": "top-down traversal of the binary tree (round 1's definition); `executed` = what the leaf-start kernels run",
+        "numerator": "top-down traversal of the binary tree by every ray (round 1's definition); `executed` = what the kernels run "
+                     "with leaf start and per-pixel candidate lists",
         "executed": {k: executed[k] for k in ("instr_per_sample", "box_tests_per_ray", "sphere_tests_per_ray")},
         "frac_executed": executed["instr_per_sample"] / instr_per_sample * achieved / peak_instr,
         "ms_per_launch": mk_ms_per_launch, "launches": mk_launches,

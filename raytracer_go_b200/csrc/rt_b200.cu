@@ -84,6 +84,8 @@ struct Workspace {
     size_t h_accum_cap = 0; // floats (pinned)
     float4 *queue = nullptr; // staged mode: 2 (ping-pong) x 3 x capacity float4 (origin, direction, throughput)
     size_t queue_cap = 0;    // elements in total
+    uint32_t *lists = nullptr; // per-pixel candidate lists of the primary stage (RT_LIST_WORDS words per pixel of a pixel tile)
+    size_t lists_cap = 0;      // words
     unsigned char *gather = nullptr; // rt_render_multi: tile-split image (+ sums) assembled on the root / sample-split receive buffer
     size_t gather_cap = 0;           // bytes
 };
@@ -117,9 +119,9 @@ extern "C" void rt_workspace_release(int device) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         cudaGetLastError();
-        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue && !w.gather) continue;
-        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb), cudaFree(w.queue), cudaFree(w.gather);
-        w.queue = nullptr, w.queue_cap = 0, w.gather = nullptr, w.gather_cap = 0;
+        if (!w.samples && !w.accum && !w.rgb && !w.h_rgb && !w.h_accum && !w.queue && !w.gather && !w.lists) continue;
+        cudaFree(w.samples), cudaFree(w.accum), cudaFree(w.rgb), cudaFree(w.queue), cudaFree(w.gather), cudaFree(w.lists);
+        w.queue = nullptr, w.queue_cap = 0, w.gather = nullptr, w.gather_cap = 0, w.lists = nullptr, w.lists_cap = 0;
         if (w.h_rgb) cudaFreeHost(w.h_rgb);
         if (w.h_accum) cudaFreeHost(w.h_accum);
         w.samples = nullptr, w.accum = nullptr, w.rgb = nullptr, w.h_rgb = nullptr, w.h_accum = nullptr;
@@ -774,6 +776,11 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     Workspace &ws = g_ws[s->device];
     rc = ws_reserve(ws.samples, ws.samples_cap, need);
     if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, (s->n_stages > 1 ? 6 : 3) * need);
+    // per-pixel candidate lists for the camera rays (two-stage mode): worth their one walk per pixel from a few
+    // samples per pixel on; RT_B200_PIXEL_LISTS=0 turns them off (A/B)
+    const bool use_lists = s->use_split && s->prims.size() > 0 && spp >= env_int("RT_B200_PIXEL_LISTS_MIN_SPP", 4) &&
+                           env_int("RT_B200_PIXEL_LISTS", 1) != 0;
+    if (rc == RT_OK && use_lists) rc = ws_reserve(ws.lists, ws.lists_cap, (size_t)pix_tile * RT_LIST_WORDS);
     if (rc != RT_OK) return rc;
     CU(cudaMemsetAsync(s->d_stats, 0, RT_N_STATS * sizeof(unsigned long long), s->stream));
     RC(dbg_begin(s, need, need, n_pix, s->n_images, s->n_perlins));
@@ -799,6 +806,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.queue_o = ws.queue, p.queue_stride = need; // launch_split fills the per-stage pointers
     p.queue_d = p.queue_t = nullptr, p.queue_count = s->d_queue_count;
     p.in_o = p.in_d = p.in_t = nullptr, p.in_count = nullptr, p.stage_depth = 0;
+    p.lists = nullptr;
     const bool balance = env_int("RT_B200_PASS_BALANCE", 0) != 0;
     uint64_t n_passes_total = 0;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_tile) {
@@ -806,6 +814,15 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
         // RT_B200_PASS_BALANCE=1 makes the passes equal (500 spp at 82 per pass = 7 passes of 71-72 instead of
         // 6 x 82 + 8); measured 0.3 % slower than the greedy split (profiles/r01y), so it is off by default
         const uint32_t n_passes = ((uint32_t)spp + spp_pass_max - 1) / spp_pass_max;
+        if (use_lists) { // one beam walk per pixel of the tile, shared by all its samples
+            p.pixel_begin = pb;
+            p.lists = nullptr;
+            if (s->has_quads) pixel_candidates_kernel<true><<<(np + 127) / 128, 128, 0, s->stream>>>(p, np, ws.lists);
+            else pixel_candidates_kernel<false><<<(np + 127) / 128, 128, 0, s->stream>>>(p, np, ws.lists);
+            CU(cudaGetLastError());
+            p.lists = ws.lists;
+            *launches += 1;
+        }
         for (uint32_t k0 = 0, pass = 0, sp = 0; k0 < (uint32_t)spp; k0 += sp, pass++) {
             sp = balance ? ((uint32_t)spp - k0 + (n_passes - pass) - 1) / (n_passes - pass)
                          : std::min(spp_pass_max, (uint32_t)spp - k0);

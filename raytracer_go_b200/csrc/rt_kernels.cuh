@@ -150,6 +150,9 @@ struct RenderParams {
     // stage k > 0 of the staged mode reads the survivors of stage k-1 here (same layout)
     const float4 *in_o, *in_d, *in_t;
     const unsigned int *in_count;
+    // per-pixel candidate lists of the call's pixel tile (pixel_candidates_kernel), nullptr = none: RT_LIST_WORDS words per
+    // pixel, [count | slots...]; count RT_LIST_OVERFLOW = too many candidates, traverse the tree for that pixel
+    const uint32_t *lists;
     int stage_depth; // segments already traced for the paths a stage kernel processes
     size_t queue_stride; // elements per queue array (host-side bookkeeping)
 };
@@ -174,6 +177,8 @@ __device__ __forceinline__ uint32_t image_pixel(const RenderParams &p, uint32_t 
 }
 
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
+#define RT_LIST_WORDS 16u /* one 64-byte line per pixel: count + up to 15 candidate slots */
+#define RT_LIST_OVERFLOW 0xFFFFFFFFu
 #define RT_MAX_STAGES 8 /* coherent stage kernels before the megakernel (staged mode) */
 
 // BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
@@ -387,7 +392,16 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
                 }
             }
             HitRec h;
-            trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+            const uint32_t *list = nullptr;
+            uint32_t n_list = RT_LIST_OVERFLOW;
+            if (FIRST && p.lists != nullptr) { // the candidates of this path's pixel (camera rays only)
+                list = p.lists + (size_t)fast_div(idx, p.div_spp) * RT_LIST_WORDS;
+                n_list = list[0];
+            }
+            if (FIRST && n_list != RT_LIST_OVERFLOW)
+                trace_candidates<COUNT, QUADS>(list + 1, n_list, sph, meta, quads, o, d, 0.001f, INFINITY, h, &wc);
+            else
+                trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
                                                FIRST ? nullptr : chains, start);
             n_rays++;
             hit_slot = h.slot;
@@ -472,6 +486,29 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
         for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
         if (lane == 0 && x) atomicAdd(p.stats + q, x);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-pixel candidate lists (primary stage)
+// ---------------------------------------------------------------------------------------------
+// Every camera ray of a pixel — all samples of all passes — starts on the defocus disk and passes through the pixel's
+// footprint, so the primitives ANY of them can hit are few (C2: 4.3 on average, profiles/experiments/r01_pixel_beam_*).
+// One thread per pixel walks the BVH once with the pixel's beam (rt_trace.h: beam_box_test, conservative interval
+// arithmetic) and writes the slots of the leaves it reaches; the primary stage then tests a path's camera ray against
+// that list (trace_candidates) instead of traversing the tree 500 times per pixel.  The closest hit is an argmin over
+// all primitives, hence also over any superset of the ones a ray can hit: results are unchanged, bit for bit.
+// A pixel with more than RT_LIST_WORDS-1 candidates is marked RT_LIST_OVERFLOW and keeps the traversal.
+template <bool QUADS>
+__global__ void __launch_bounds__(128) pixel_candidates_kernel(const __grid_constant__ RenderParams p, uint32_t n_pixels,
+                                                               uint32_t *__restrict__ lists) {
+    const uint32_t pp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pp >= n_pixels) return;
+    const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
+    const int j = (int)(pixel / (uint32_t)p.cam.width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+    const Beam b = pixel_beam(p.cam, i, j);
+    uint32_t *out = lists + (size_t)pp * RT_LIST_WORDS;
+    const uint32_t n = beam_candidates<QUADS>(p.sc.nodes, p.sc.root_ref, b, out + 1, RT_LIST_WORDS - 1);
+    out[0] = n > RT_LIST_WORDS - 1 ? RT_LIST_OVERFLOW : n;
 }
 
 // accum[pixel] (+)= sum_k samples[(pixel - pixel_begin) * spp_pass + k], k ascending: the FP32

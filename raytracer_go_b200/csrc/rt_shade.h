@@ -90,6 +90,25 @@ RT_HD void generate_ray(const DevCamera &c, PathRng &rng, int i, int j, V3 &orig
     dir = pc - origin;
 }
 
+// The beam of pixel (i, j): every ray generate_ray can return for it, whatever the sample (rt_trace.h: Beam).  Origins
+// lie in the box around the camera centre that holds the defocus parallelogram (|sx|, |sy| <= 1), the points aimed
+// at in the pixel's footprint (|dx|, |dy| <= 0.5) around the centre formed exactly as generate_ray forms it; both are
+// widened by RT_BEAM_EPS of the magnitudes involved — the float32 roundings of generate_ray's sums are ~1e-7 of them.
+RT_HD Beam pixel_beam(const DevCamera &c, int i, int j) {
+    V3 pc = c.pixel00;
+    pc = pc + c.du * (float)i;
+    pc = pc + c.dv * (float)j;
+    const V3 hw = v3(0.5f * (fabsf(c.du.x) + fabsf(c.dv.x)), 0.5f * (fabsf(c.du.y) + fabsf(c.dv.y)), 0.5f * (fabsf(c.du.z) + fabsf(c.dv.z)));
+    const V3 ow = c.defocus ? v3(fabsf(c.disk_u.x) + fabsf(c.disk_v.x), fabsf(c.disk_u.y) + fabsf(c.disk_v.y), fabsf(c.disk_u.z) + fabsf(c.disk_v.z))
+                            : v3(0, 0, 0);
+    const V3 m = v3(RT_BEAM_EPS * (fabsf(pc.x) + fabsf(c.center.x) + hw.x + ow.x), RT_BEAM_EPS * (fabsf(pc.y) + fabsf(c.center.y) + hw.y + ow.y),
+                    RT_BEAM_EPS * (fabsf(pc.z) + fabsf(c.center.z) + hw.z + ow.z));
+    Beam b;
+    b.olo = c.center - ow - m, b.ohi = c.center + ow + m;
+    b.dlo = (pc - hw - m) - b.ohi, b.dhi = (pc + hw + m) - b.olo;
+    return b;
+}
+
 struct HitInfo {
     V3 point, normal;
     bool front;

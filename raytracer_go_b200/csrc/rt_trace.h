@@ -371,4 +371,112 @@ RT_HD void trace_closest(const F4 *__restrict__ nodes, const F4 *__restrict__ sp
     hit.slot = best_slot;
 }
 
+// Closest hit among an explicit list of candidate slots (bit 30 = quad slot, as HitRec.slot): the leaf loop of
+// trace_closest without the tree.  World.Hit's answer is the argmin over (accepted root, object index) of ALL
+// primitives, so it is also the argmin over any SUPERSET of the primitives the ray can hit — which is what the
+// per-pixel candidate lists of the primary stage are (pixel_candidates_kernel in rt_kernels.cuh).
+template <bool COUNT, bool QUADS>
+RT_HD void trace_candidates(const uint32_t *__restrict__ list, uint32_t n, const F4 *__restrict__ sph,
+                            const I2 *__restrict__ meta, const F4 *__restrict__ quads, V3 o, V3 d, float tmin, float tmax,
+                            HitRec &hit, WorkCounters *wc) {
+    const float a = lensq(d);
+    float tbest = tmax;
+    uint32_t best_slot = RT_REF_NONE;
+    int32_t best_id = 0x7fffffff;
+    bool have_id = false;
+    if (COUNT) wc->sphere_tests += n;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t hs = list[k];
+        float t;
+        if (QUADS && (hs & RT_HIT_QUAD)) {
+            if (!quad_candidate(quads + (size_t)RT_QUAD_F4 * (hs & ~RT_HIT_QUAD), o, d, tmin, tbest, t)) continue;
+        } else {
+            const F4 sp = sph[hs];
+            if (!sphere_candidate(sp, o, d, a, tmin, t)) continue;
+        }
+        if (t < tbest) {
+            tbest = t, best_slot = hs, have_id = false;
+        } else if (t == tbest && best_slot != RT_REF_NONE) { // exact tie: the earlier object (hittables.go:59-69)
+            if (!have_id) best_id = slot_object_id(best_slot, meta, quads), have_id = true;
+            const int32_t id = slot_object_id(hs, meta, quads);
+            if (id < best_id) best_slot = hs, best_id = id;
+        }
+    }
+    hit.t = tbest;
+    hit.slot = best_slot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// beams: every camera ray of one pixel at once (interval arithmetic), for the per-pixel candidate lists
+// ---------------------------------------------------------------------------------------------
+// All rays of a pixel start in the box [olo, ohi] (the defocus disk around the camera centre) and have directions in
+// the box [dlo, dhi] (pixel footprint minus origin box).  At ray parameter t >= 0 every one of them is inside the box
+// [olo + t*dlo, ohi + t*dhi]; a ray that passes the kernels' slab test of a node box is inside that node box at some t,
+// so the two boxes overlap on all three axes at that t.  beam_box_test asks whether such a t exists: per axis two
+// half-lines in t (olo + t*dlo <= max and ohi + t*dhi >= min), intersected.  The node box is widened by RT_BEAM_EPS
+// of the magnitudes involved — two orders of magnitude more than the rounding of box_test (a few 2^-23 of
+// |c*inv| + |o*inv| + h*|inv|, approximate reciprocal included).  A box the beam test rejects is rejected by box_test
+// for every ray of the pixel, so the subtree below it cannot contribute a hit.
+#define RT_BEAM_EPS 1e-5f
+struct Beam {
+    V3 olo, ohi, dlo, dhi;
+};
+// one axis: narrows [t0, t1]; false = the beam never overlaps the slab
+RT_HD bool beam_axis(float c, float h, float olo, float ohi, float dlo, float dhi, float &t0, float &t1) {
+    const float e = RT_BEAM_EPS * (fabsf(c) + h + fmaxf(fabsf(olo), fabsf(ohi))) + 1e-30f;
+    const float A = (c + h + e) - olo; // olo + t*dlo <= max
+    const float B = (c - h - e) - ohi; // ohi + t*dhi >= min
+    if (dlo > 0.0f) t1 = fminf(t1, A / dlo);
+    else if (dlo < 0.0f) t0 = fmaxf(t0, A / dlo);
+    else if (A < 0.0f) return false;
+    if (dhi > 0.0f) t0 = fmaxf(t0, B / dhi);
+    else if (dhi < 0.0f) t1 = fminf(t1, B / dhi);
+    else if (B > 0.0f) return false;
+    return true;
+}
+RT_HD bool beam_box_test(const F4 &c, const F4 &h, const Beam &b) {
+    float t0 = 0.0f, t1 = INFINITY;
+    if (!beam_axis(c.x, h.x, b.olo.x, b.ohi.x, b.dlo.x, b.dhi.x, t0, t1)) return false;
+    if (!beam_axis(c.y, h.y, b.olo.y, b.ohi.y, b.dlo.y, b.dhi.y, t0, t1)) return false;
+    if (!beam_axis(c.z, h.z, b.olo.z, b.ohi.z, b.dlo.z, b.dhi.z, t0, t1)) return false;
+    return !(t0 > t1 * (1.0f + RT_BEAM_EPS)); // (NaN never culls: fminf / fmaxf ignore it)
+}
+
+// Walks the tree (global-memory layout, 32 bytes per node) with a beam and writes the slots of every leaf it reaches
+// (bit 30 set for quad slots) to out[0..cap); returns how many there are — more than cap means the list overflowed.
+template <bool QUADS>
+RT_HD uint32_t beam_candidates(const F4 *__restrict__ nodes, uint32_t root_ref, const Beam &b, uint32_t *out, uint32_t cap) {
+    uint32_t n = 0;
+    LocalStack<64> stack;
+    stack.reset();
+    uint32_t ref = root_ref;
+    for (;;) {
+        while (!(ref & RT_LEAF)) {
+            const F4 *np = nodes + 2 * (size_t)ref;
+            const F4 l0 = np[0], l1 = np[1], r0 = np[2], r1 = np[3];
+            const bool hl = beam_box_test(l0, l1, b), hr = beam_box_test(r0, r1, b);
+            const uint32_t lref = as_uint(l0.w), rref = as_uint(r0.w);
+            if (hl && hr) {
+                stack.push(rref);
+                ref = lref;
+            } else if (hl) {
+                ref = lref;
+            } else if (hr) {
+                ref = rref;
+            } else {
+                ref = stack.pop();
+            }
+        }
+        if (ref == RT_REF_NONE) break;
+        const uint32_t first = (ref & RT_LEAF_SLOT_MASK) >> 3, count = (ref & 7u) + 1;
+        const uint32_t flag = (QUADS && (ref & RT_LEAF_QUAD)) ? RT_HIT_QUAD : 0u;
+        for (uint32_t s = first; s < first + count; s++) {
+            if (n < cap) out[n] = s | flag;
+            n++;
+        }
+        ref = stack.pop();
+    }
+    return n;
+}
+
 #endif // RT_TRACE_H

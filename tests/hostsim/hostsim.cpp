@@ -477,3 +477,50 @@ extern "C" int64_t hs_beam_stats(const rt_scene_desc *d, const rt_camera *cam, u
     }
     return n;
 }
+
+// The per-pixel candidate lists of the primary stage (rt_kernels.cuh: pixel_candidates_kernel) replayed on the host
+// with the very functions the kernel calls (pixel_beam, beam_candidates): for `n_pixels` pixels starting at
+// pixel_begin (stride pixel_stride) and `spp` camera rays each, checks that (1) the closest hit of every ray is in the
+// pixel's list and (2) trace_candidates over the list returns exactly what the tree traversal returns.
+// out[0] = pixels, out[1] = sum of list lengths, out[2] = longest list, out[3] = rays whose hit is missing from the
+// list, out[4] = rays where the two traces differ, out[5] = lists longer than `cap`.
+extern "C" int hs_pixel_candidates(const rt_scene_desc *d, const rt_camera *cam, uint64_t seed, int64_t pixel_begin,
+                                   int64_t n_pixels, int64_t pixel_stride, int32_t spp, int max_leaf, uint32_t cap, double *out) {
+    HostScene s;
+    load(d, max_leaf, 0, &s);
+    DevCamera c = make_dev_camera(*cam);
+    const bool quads = !s.bvh.quad_prim.empty();
+    for (int k = 0; k < 6; k++) out[k] = 0;
+    std::vector<uint32_t> list(4096);
+    for (int64_t pp = 0; pp < n_pixels; pp++) {
+        const int64_t pix = pixel_begin + pp * pixel_stride;
+        const int i = (int)(pix % cam->width), j = (int)(pix / cam->width);
+        const Beam b = pixel_beam(c, i, j);
+        const uint32_t n = quads ? beam_candidates<true>(s.bvh.dev_nodes.data(), s.bvh.root_ref, b, list.data(), (uint32_t)list.size())
+                                 : beam_candidates<false>(s.bvh.dev_nodes.data(), s.bvh.root_ref, b, list.data(), (uint32_t)list.size());
+        out[0] += 1, out[1] += n, out[2] = std::max(out[2], (double)n);
+        if (n > cap) out[5] += 1;
+        if (n > list.size()) return -1;
+        for (int k = 0; k < spp; k++) {
+            PathRng rng;
+            rng.init(seed, (uint32_t)pix, (uint32_t)k);
+            V3 o, dir;
+            generate_ray(c, rng, i, j, o, dir);
+            LocalStack<64> stack;
+            HitRec h, hc;
+            WorkCounters wc{0, 0};
+            if (quads) {
+                trace_closest<LocalStack<64>, false, true>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref, o, dir,
+                                                           0.001f, INFINITY, stack, h, &wc, s.bvh.quad.data());
+                trace_candidates<false, true>(list.data(), n, s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.quad.data(), o, dir, 0.001f, INFINITY, hc, &wc);
+            } else {
+                trace_closest<LocalStack<64>, false, false>(s.bvh.dev_nodes.data(), s.bvh.sph.data(), s.bvh.meta.data(), s.bvh.root_ref, o, dir,
+                                                            0.001f, INFINITY, stack, h, &wc);
+                trace_candidates<false, false>(list.data(), n, s.bvh.sph.data(), s.bvh.meta.data(), nullptr, o, dir, 0.001f, INFINITY, hc, &wc);
+            }
+            if (h.slot != RT_REF_NONE && std::find(list.begin(), list.begin() + n, h.slot) == list.begin() + n) out[3] += 1;
+            if (h.slot != hc.slot || (h.slot != RT_REF_NONE && as_uint(h.t) != as_uint(hc.t))) out[4] += 1;
+        }
+    }
+    return 0;
+}

@@ -377,3 +377,42 @@ def test_leaf_start_on_quads_and_fuzz_scenes(hs, orc):
     rids, rts = orc.trace(s, o, d)
     assert np.array_equal(ids, rids)
     assert np.array_equal(ts[rids >= 0].view(np.uint32), rts[rids >= 0].view(np.uint32))
+
+
+def hs_pixel_candidates(hs, scene, opts, n_pixels, stride, spp, begin=0, cap=15):
+    cam = api.camera_from_options(opts) if False else None  # (the camera comes from the oracle: no GPU library needed)
+    from oracle import pyoracle as orc
+    cam = orc.camera_from_options(opts)
+    desc, keep = scene.to_desc()
+    out = (C.c_double * 6)()
+    rc = hs.hs_pixel_candidates(C.byref(desc), C.byref(cam), C.c_uint64(123), C.c_int64(begin), C.c_int64(n_pixels),
+                                C.c_int64(stride), spp, 4, cap, out)
+    assert rc == 0
+    return dict(pixels=out[0], mean=out[1] / max(1.0, out[0]), longest=out[2], missing=out[3], differ=out[4], overflow=out[5])
+
+
+@pytest.mark.parametrize("name", ["random", "random_wide", "cornell", "mixed", "perlin", "earth", "no_defocus"])
+def test_pixel_candidate_lists_are_supersets(hs, name):
+    """Per-pixel candidate lists of the primary stage (pixel_beam + beam_candidates, the functions
+    pixel_candidates_kernel calls): for every camera ray drawn for a pixel the closest hit is in the pixel's list, and
+    trace_candidates over the list returns the tree traversal's answer bit for bit.  Also pins the list statistics the
+    design relies on (a handful of candidates per pixel, overflows rare)."""
+    opts, n, stride, spp = scenes.camera_options(400, 1), 400 * 225 // 7, 7, 8
+    if name == "random":
+        s = scenes.random_scene()
+    elif name == "random_wide":     # 90 degrees: direction intervals straddle zero on two axes in the image centre
+        s, opts = scenes.random_scene(), scenes.camera_options(400, 1, vfov_deg=90.0, look_from=(0.5, 0.3, 0.5), look_at=(0.5, 0.3, -5))
+    elif name == "no_defocus":
+        s, opts = scenes.random_scene(), scenes.camera_options(400, 1, defocus_deg=0.0)
+    elif name == "cornell":
+        s, opts, n, stride = scenes.cornell_box_scene(), scenes.cornell_camera_options(200, 1), 200 * 200 // 3, 3
+    elif name == "mixed":
+        s = scenes.mixed_scene()
+    elif name == "perlin":
+        s, opts = scenes.perlin_demo_scene(), scenes.perlin_camera_options(400, 1)
+    else:
+        s, opts = scenes.earth_scene(), scenes.camera_options(400, 1, look_from=(0, 0, -12), defocus_deg=0.0)
+    r = hs_pixel_candidates(hs, s, opts, n, stride, spp)
+    assert r["pixels"] == n and r["missing"] == 0 and r["differ"] == 0
+    if name == "random":
+        assert 3.5 < r["mean"] < 6.0 and r["longest"] <= 24 and r["overflow"] < 0.01 * n
