@@ -293,7 +293,8 @@ typedef struct rt_bvh_info {
     uint32_t in_shared_memory; /* 1 when the scene fits the per-CTA shared-memory staging path */
     float box_pad_min, box_pad_max;
     uint32_t root_ref;
-    uint32_t reserved;
+    uint32_t built_on_device; /* 1: the tree was built on the GPU (large sphere-only scenes; Morton-order linear BVH with
+                                 leaf collapse) — nodes_out then holds the boxes as the kernels test them; 0: binned SAH on the host */
 } rt_bvh_info;
 int rt_scene_bvh_info(const rt_scene *scene, rt_bvh_info *out);
 int rt_scene_bvh_copy(const rt_scene *scene, uint32_t *nodes_out /* n_nodes*8 */,

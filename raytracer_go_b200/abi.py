@@ -96,7 +96,7 @@ class rt_stats(C.Structure):
 class rt_bvh_info(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_slots", C.c_uint64), ("max_depth", C.c_uint32),
                 ("in_shared_memory", C.c_uint32), ("box_pad_min", C.c_float),
-                ("box_pad_max", C.c_float), ("root_ref", C.c_uint32), ("reserved", C.c_uint32)]
+                ("box_pad_max", C.c_float), ("root_ref", C.c_uint32), ("built_on_device", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/rt_b200.h declares.

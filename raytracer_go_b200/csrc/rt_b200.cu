@@ -61,6 +61,7 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 #include "rt_kernels.cuh"
+#include "bvh_device.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // host side: per-device workspace, shared by all scene handles of the process
@@ -188,6 +189,11 @@ struct rt_scene {
     DevPerlin *d_perlins = nullptr;
     std::vector<uint16_t *> d_texels;
     uint32_t n_images = 0, n_perlins = 0;
+    size_t n_prims = 0;            // hittables of the scene (the host copy `prims` is empty for a device-built tree)
+    bool device_built = false;     // the BVH was built on the GPU (bvh_device.cuh); `bvh` holds no host arrays then
+    rt_sphere *d_raw = nullptr;    // device-built: the caller's spheres and IDs, kept for rebuilds with a larger radius
+    uint32_t *d_raw_ids = nullptr;
+    BdStats dev_stats{};           // device-built: statistics of the last build
     int grid_cache[2] = {0, 0};  // persistent grid size of the plain / counting megakernel
     size_t smem_cache[2] = {0, 0};
     unsigned int *d_counter = nullptr;
@@ -303,6 +309,7 @@ static void free_scene(rt_scene *s) {
     cudaStream_t st = s->own_stream;
     scene_free(s->d_nodes, st), scene_free(s->d_sph, st), scene_free(s->d_mats, st), scene_free(s->d_meta, st);
     scene_free(s->d_images, st), scene_free(s->d_quads, st), scene_free(s->d_perlins, st), scene_free(s->d_chains, st);
+    scene_free(s->d_raw, st), scene_free(s->d_raw_ids, st);
     for (auto p : s->d_texels) scene_free(p, st);
     scene_free(s->d_counter, st), scene_free(s->d_stats, st), scene_free(s->d_queue_count, st);
     for (auto e : s->events) cudaEventDestroy(e);
@@ -342,6 +349,73 @@ static int host_scene_parts(const rt_scene_desc *desc, HostSceneParts *h) {
     return RT_OK;
 }
 
+// Large sphere-only scenes get their tree from the GPU (bvh_device.cuh).  RT_B200_DEVICE_BVH: 0 never, 1 (default)
+// from RT_B200_DEVICE_BVH_MIN spheres on (50 000), 2 whenever the scene has no quads (tests run the small parity
+// scenes through the device builder that way).
+static bool want_device_bvh(const rt_scene_desc *d) {
+    const int mode = env_int("RT_B200_DEVICE_BVH", 1);
+    if (mode == 0 || d->n_quads != 0 || d->n_spheres < 2) return false;
+    return mode >= 2 || d->n_spheres >= (uint64_t)std::max(2, env_int("RT_B200_DEVICE_BVH_MIN", 50000));
+}
+
+// (Re)build the device tree of a device-built scene for s->origin_radius into the handle's buffers.
+static int device_bvh_build(rt_scene *s) {
+    cudaError_t e = device_build_bvh(s->d_raw, s->d_raw_ids, (uint32_t)s->n_prims, s->center, (double)s->origin_radius,
+                                     // leaves of <= 2 spheres: measured on C4, 1 / 2 / 3 / 4 / 6 per leaf = 1329 / 1324 / 1307 / 1308 / 1289
+                                     // Msamples/s (profiles/r02o); Morton-consecutive spheres make worse leaves than the SAH builder's
+                                     std::max(1, std::min(env_int("RT_B200_MAX_LEAF", 2), RT_MAX_LEAF)), s->d_nodes, s->d_sph, s->d_meta,
+                                     s->stream, &s->dev_stats);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA, "device BVH build: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+// Uploads the spheres and builds the tree on the GPU.  Returns RT_OK with s->device_built = false when the scene turns
+// out not to suit the device builder (too many huge spheres, a tree deeper than the traversal stack): the caller then
+// uses the host builder.
+static int scene_create_device_bvh(const rt_scene_desc *desc, int device, rt_scene *s) {
+    const size_t n = desc->n_spheres;
+    if (desc->sphere_ids) { // must be a permutation of 0..n-1 (load_scene_prims checks the same on the host path)
+        std::vector<bool> seen(n, false);
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t id = desc->sphere_ids[i];
+            if (id >= n || seen[id]) return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids / quad_ids are not a permutation of 0..n_hittables-1");
+            seen[id] = true;
+        }
+    }
+    // the scene's centre and typical extent from a strided sample (exact medians of 1 M centres cost 13 ms and only
+    // feed the padding rule, which needs a reference point, not THE median)
+    {
+        ScenePrims sample;
+        const size_t stride = std::max<size_t>(1, n / 65536);
+        for (size_t i = 0; i < n; i += stride) sample.spheres.push_back(desc->spheres[i]);
+        sample.sphere_ids.resize(sample.spheres.size());
+        compute_scene_center(sample, s->center, &s->extent90, nullptr);
+    }
+    s->fixed_radius = desc->ray_origin_radius > 0;
+    s->origin_radius = s->fixed_radius ? desc->ray_origin_radius : (float)(2.0 * s->extent90);
+    s->n_prims = n, s->has_quads = false;
+    RC(scene_alloc(&s->d_raw, n * sizeof(rt_sphere), device, s->stream));
+    CU(cudaMemcpyAsync(s->d_raw, desc->spheres, n * sizeof(rt_sphere), cudaMemcpyHostToDevice, s->stream));
+    if (desc->sphere_ids) {
+        RC(scene_alloc(&s->d_raw_ids, n * 4, device, s->stream));
+        CU(cudaMemcpyAsync(s->d_raw_ids, desc->sphere_ids, n * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    RC(scene_alloc(&s->d_nodes, n * 64, device, s->stream)); // at most n pairs of nodes
+    RC(scene_alloc(&s->d_sph, n * 16, device, s->stream));
+    RC(scene_alloc(&s->d_meta, n * 8, device, s->stream));
+    RC(device_bvh_build(s));
+    if (s->dev_stats.n_large > BD_MAX_LARGE || s->dev_stats.max_depth + 2 > RT_LOCAL_STACK) { // not a scene for this builder
+        scene_free(s->d_raw, s->stream), scene_free(s->d_raw_ids, s->stream), scene_free(s->d_nodes, s->stream);
+        scene_free(s->d_sph, s->stream), scene_free(s->d_meta, s->stream);
+        s->d_raw = nullptr, s->d_raw_ids = nullptr, s->d_nodes = nullptr, s->d_sph = nullptr, s->d_meta = nullptr;
+        s->n_prims = 0;
+        return RT_OK;
+    }
+    s->surface_extent = (double)__builtin_bit_cast(float, s->dev_stats.surface_extent);
+    s->device_built = true;
+    return RT_OK;
+}
+
 static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s, const HostSceneParts *pre = nullptr) {
     s->device = device;
     CU(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -359,7 +433,13 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
         fprintf(stderr, "[scene] %-14s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     };
-    if (pre) { // built once by the caller (rt_render_multi); every handle keeps its own copy (refits are per handle)
+    if (!pre && want_device_bvh(desc)) {
+        RC(scene_create_device_bvh(desc, device, s));
+        lap(s->device_built ? "device bvh" : "device bvh (declined)");
+    }
+    if (s->device_built) {
+        // nothing to do on the host
+    } else if (pre) { // built once by the caller (rt_render_multi); every handle keeps its own copy (refits are per handle)
         s->prims = pre->prims, s->bvh = pre->bvh;
         s->center[0] = pre->center[0], s->center[1] = pre->center[1], s->center[2] = pre->center[2];
         s->extent90 = pre->extent90, s->surface_extent = pre->surface_extent;
@@ -379,29 +459,47 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
                        want_leaf_start(s->prims.size()));
         lap("bvh build");
     }
+    if (!s->device_built) s->n_prims = s->prims.size();
 
+    // materials: folded with their textures into 32-byte records — on the host, or (device-built scenes, which tend
+    // to have one material per sphere) by a kernel from the raw arrays
     std::vector<F4> mats;
-    pack_materials(desc, &mats);
+    const bool mats_on_device = s->device_built && desc->n_materials >= 4096;
+    if (!mats_on_device) pack_materials(desc, &mats);
     lap("materials");
 
     // device nodes = the tree's nodes + the walk pairs of the leaf-start chains
-    const size_t n_nodes = s->bvh.dev_nodes.size() / 2, n_slots = s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
+    const size_t n_nodes = s->device_built ? 2 * (size_t)s->dev_stats.n_pairs : s->bvh.dev_nodes.size() / 2;
+    const size_t n_slots = s->device_built ? s->n_prims : s->bvh.sph.size(), n_qslots = s->bvh.quad_prim.size();
     RC(scene_alloc(&s->d_quads, std::max<size_t>(1, n_qslots) * 16 * RT_QUAD_F4, device, s->stream));
     if (n_qslots)
         CU(cudaMemcpyAsync(s->d_quads, s->bvh.quad.data(), n_qslots * 16 * RT_QUAD_F4, cudaMemcpyHostToDevice, s->stream));
-    RC(scene_alloc(&s->d_nodes, std::max<size_t>(1, n_nodes) * 32, device, s->stream));
-    RC(scene_alloc(&s->d_sph, std::max<size_t>(1, n_slots) * 16, device, s->stream));
-    RC(scene_alloc(&s->d_meta, std::max<size_t>(1, n_slots) * 8, device, s->stream));
-    RC(scene_alloc(&s->d_mats, std::max<size_t>(1, mats.size()) * 16, device, s->stream));
-    {
+    if (!s->device_built) {
+        RC(scene_alloc(&s->d_nodes, std::max<size_t>(1, n_nodes) * 32, device, s->stream));
+        RC(scene_alloc(&s->d_sph, std::max<size_t>(1, n_slots) * 16, device, s->stream));
+        RC(scene_alloc(&s->d_meta, std::max<size_t>(1, n_slots) * 8, device, s->stream));
         int rc = upload_nodes(s);
         if (rc != RT_OK) return rc;
+        if (n_slots) {
+            CU(cudaMemcpyAsync(s->d_sph, s->bvh.sph.data(), n_slots * 16, cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(s->d_meta, s->bvh.meta.data(), n_slots * 8, cudaMemcpyHostToDevice, s->stream));
+        }
     }
-    if (n_slots) {
-        CU(cudaMemcpyAsync(s->d_sph, s->bvh.sph.data(), n_slots * 16, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(s->d_meta, s->bvh.meta.data(), n_slots * 8, cudaMemcpyHostToDevice, s->stream));
+    RC(scene_alloc(&s->d_mats, std::max<size_t>(1, (size_t)desc->n_materials) * 32, device, s->stream));
+    if (mats_on_device) {
+        rt_material *d_m = nullptr;
+        rt_texture *d_t = nullptr;
+        RC(scene_alloc(&d_m, (size_t)desc->n_materials * sizeof(rt_material), device, s->stream));
+        RC(scene_alloc(&d_t, std::max<size_t>(1, desc->n_textures) * sizeof(rt_texture), device, s->stream));
+        CU(cudaMemcpyAsync(d_m, desc->materials, (size_t)desc->n_materials * sizeof(rt_material), cudaMemcpyHostToDevice, s->stream));
+        if (desc->n_textures)
+            CU(cudaMemcpyAsync(d_t, desc->textures, (size_t)desc->n_textures * sizeof(rt_texture), cudaMemcpyHostToDevice, s->stream));
+        bd_pack_materials<<<(desc->n_materials + 255) / 256, 256, 0, s->stream>>>(d_m, d_t, desc->n_materials, s->d_mats);
+        CU(cudaGetLastError());
+        scene_free(d_m, s->stream), scene_free(d_t, s->stream);
+    } else if (!mats.empty()) {
+        CU(cudaMemcpyAsync(s->d_mats, mats.data(), mats.size() * 16, cudaMemcpyHostToDevice, s->stream));
     }
-    if (!mats.empty()) CU(cudaMemcpyAsync(s->d_mats, mats.data(), mats.size() * 16, cudaMemcpyHostToDevice, s->stream));
     if (!s->bvh.chains.empty()) { // leaf start: chains, then the per-slot chain offsets of spheres and quads, in one buffer
         const size_t nc = s->bvh.chains.size(), total = nc + n_slots + n_qslots;
         RC(scene_alloc(&s->d_chains, total * 4, device, s->stream));
@@ -460,12 +558,12 @@ static int scene_create_impl(const rt_scene_desc *desc, int device, rt_scene *s,
     s->dev.nodes = s->d_nodes, s->dev.sph = s->d_sph, s->dev.meta = s->d_meta, s->dev.mats = s->d_mats;
     s->dev.tex.images = s->d_images, s->dev.tex.perlins = s->d_perlins;
     s->dev.quads = s->d_quads, s->dev.n_quad_slots = (uint32_t)n_qslots;
-    s->dev.root_ref = s->bvh.root_ref;
+    s->dev.root_ref = s->device_built ? s->dev_stats.root_ref : s->bvh.root_ref;
     s->dev.n_nodes = (uint32_t)n_nodes, s->dev.n_slots = (uint32_t)n_slots, s->dev.n_mats = desc->n_materials;
     s->n_images = desc->n_images, s->n_perlins = desc->n_perlins;
-    s->dev.stack_depth = s->bvh.max_depth + 2;
-    if (s->dev.stack_depth > RT_LOCAL_STACK) // cannot happen: the builder balances the tree below depth 30
-        return fail(RT_ERR_INTERNAL, "BVH depth %u exceeds the traversal stack (%d)", s->bvh.max_depth, RT_LOCAL_STACK);
+    s->dev.stack_depth = (s->device_built ? s->dev_stats.max_depth : s->bvh.max_depth) + 2;
+    if (s->dev.stack_depth > RT_LOCAL_STACK) // cannot happen: the host builder balances the tree below depth 30, a deeper device-built tree was declined
+        return fail(RT_ERR_INTERNAL, "BVH depth %u exceeds the traversal stack (%d)", s->dev.stack_depth - 2, RT_LOCAL_STACK);
     // 512-thread CTAs, two per SM: 32 warps at 64 registers.  Measured against 256 x 3 (24 warps at 80
     // registers): C2 +6 %, Cornell box +3 % (profiles/r01aj, r01ak); the kernels wait on fixed-latency
     // dependencies and shared-memory loads, so 8 more warps per SM buy more than 16 more registers.
@@ -547,8 +645,14 @@ extern "C" int rt_scene_set_stream(rt_scene *scene, void *cuda_stream) {
 // primitive whose nearest point is origin_dist + surface_extent away.
 static int ensure_origin_radius(rt_scene *s, double origin_dist) {
     const double needed = origin_dist + s->surface_extent;
-    if (s->fixed_radius || needed <= s->origin_radius || s->prims.size() == 0) return RT_OK;
+    if (s->fixed_radius || needed <= s->origin_radius || s->n_prims == 0) return RT_OK;
     s->origin_radius = (float)(needed * 1.25);
+    if (s->device_built) { // the same build with the larger padding: same Morton order, same topology, same buffers
+        RC(device_bvh_build(s));
+        if (2 * (size_t)s->dev_stats.n_pairs != s->dev.n_nodes || s->dev_stats.root_ref != s->dev.root_ref)
+            return fail(RT_ERR_INTERNAL, "device BVH rebuild changed the topology");
+        return RT_OK;
+    }
     refit_flat_bvh(s->prims, s->origin_radius, &s->bvh);
     int rc = upload_nodes(s);
     if (rc != RT_OK) return rc;
@@ -778,7 +882,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, (s->n_stages > 1 ? 6 : 3) * need);
     // per-pixel candidate lists for the camera rays (two-stage mode): worth their one walk per pixel from a few
     // samples per pixel on; RT_B200_PIXEL_LISTS=0 turns them off (A/B)
-    const bool use_lists = s->use_split && s->prims.size() > 0 && spp >= env_int("RT_B200_PIXEL_LISTS_MIN_SPP", 4) &&
+    const bool use_lists = s->use_split && s->n_prims > 0 && spp >= env_int("RT_B200_PIXEL_LISTS_MIN_SPP", 4) &&
                            env_int("RT_B200_PIXEL_LISTS", 1) != 0;
     if (rc == RT_OK && use_lists) rc = ws_reserve(ws.lists, ws.lists_cap, (size_t)pix_tile * RT_LIST_WORDS);
     if (rc != RT_OK) return rc;
@@ -1052,8 +1156,11 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
     rc = validate_desc(desc);
     if (rc != RT_OK) return rc;
     HostSceneParts parts;
-    rc = host_scene_parts(desc, &parts);
-    if (rc != RT_OK) return rc;
+    const bool per_device_build = want_device_bvh(desc); // every device builds its own tree (a few ms of GPU time)
+    if (!per_device_build) {
+        rc = host_scene_parts(desc, &parts);
+        if (rc != RT_OK) return rc;
+    }
     const bool timing = getenv("RT_B200_MULTI_TIMING") != nullptr; // host-side phases of the call, to stderr
     double t_lap = t0;
     auto lap = [&](const char *what) {
@@ -1114,7 +1221,7 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
         threads.emplace_back([&, k]() {
             Job &jj = jobs[k];
             if (jj.idle) return;
-            jj.rc = guarded([&] { return rt_scene_create_impl(desc, devs[k], &jj.scene, &parts); });
+            jj.rc = guarded([&] { return rt_scene_create_impl(desc, devs[k], &jj.scene, per_device_build ? nullptr : &parts); });
             if (jj.rc == RT_OK) {
                 Workspace &ws = g_ws[devs[k]];
                 const size_t my_acc = (size_t)jj.o.row_count * row_bytes;
@@ -1392,13 +1499,38 @@ extern "C" int rt_scene_bvh_info(const rt_scene *s, rt_bvh_info *out) {
     if (!s || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
     out->n_nodes = s->bvh.nodes.size() / 2, out->n_slots = s->bvh.sph.size();
     out->max_depth = s->bvh.max_depth, out->in_shared_memory = s->use_smem ? 1 : 0;
-    out->root_ref = s->bvh.root_ref, out->reserved = 0;
+    out->root_ref = s->bvh.root_ref, out->built_on_device = 0;
     out->box_pad_min = s->bvh.pad_min, out->box_pad_max = s->bvh.pad_max;
+    if (s->device_built) {
+        out->n_nodes = 2 * (uint64_t)s->dev_stats.n_pairs, out->n_slots = s->n_prims;
+        out->max_depth = s->dev_stats.max_depth, out->root_ref = s->dev_stats.root_ref;
+        out->built_on_device = 1;
+        out->box_pad_min = __builtin_bit_cast(float, s->dev_stats.pad_min), out->box_pad_max = __builtin_bit_cast(float, s->dev_stats.pad_max);
+    }
     return RT_OK;
 }
 
 static int rt_scene_bvh_copy_impl(const rt_scene *s, uint32_t *nodes_out, int32_t *slot_ids_out) {
     if (!s) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->device_built) { // read the tree back: boxes as the kernels test them, [c - h, c + h]
+        CU(cudaSetDevice(s->device));
+        const size_t nn = 2 * (size_t)s->dev_stats.n_pairs;
+        if (nodes_out && nn) {
+            std::vector<F4> dn(2 * nn);
+            CU(cudaMemcpy(dn.data(), s->d_nodes, dn.size() * sizeof(F4), cudaMemcpyDeviceToHost));
+            F4 *o = reinterpret_cast<F4 *>(nodes_out);
+            for (size_t i = 0; i < nn; i++) {
+                const F4 c = dn[2 * i], h = dn[2 * i + 1];
+                o[2 * i] = F4{c.x - h.x, c.y - h.y, c.z - h.z, c.w}, o[2 * i + 1] = F4{c.x + h.x, c.y + h.y, c.z + h.z, 0.0f};
+            }
+        }
+        if (slot_ids_out && s->n_prims) {
+            std::vector<I2> meta(s->n_prims);
+            CU(cudaMemcpy(meta.data(), s->d_meta, meta.size() * sizeof(I2), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < meta.size(); i++) slot_ids_out[i] = meta[i].x;
+        }
+        return RT_OK;
+    }
     if (nodes_out && !s->bvh.nodes.empty()) memcpy(nodes_out, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(F4));
     if (slot_ids_out)
         for (size_t i = 0; i < s->bvh.meta.size(); i++) slot_ids_out[i] = s->bvh.meta[i].x;

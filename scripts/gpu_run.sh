@@ -57,7 +57,7 @@ for step in "$@"; do
     configs)
       for cfg in C1 C3 C4 C5 CB; do
         extra=""; [ $cfg = C5 ] && extra="--spp 64"
-        timeout 600 python bench.py --config $cfg $extra --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_${cfg}.json 2>> gpurun_out/${TAG}_configs.err
+        timeout 600 python bench.py --config $cfg $extra --steps 3 --warmup 3 --no-cpu-baseline --no-strong > gpurun_out/${TAG}_bench_${cfg}.json 2>> gpurun_out/${TAG}_configs.err
         line $cfg gpurun_out/${TAG}_bench_${cfg}.json
       done ;;
     sweep:*)
