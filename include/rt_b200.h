@@ -118,9 +118,14 @@ typedef struct rt_scene_desc {
     uint32_t n_images;
     /* Sizes the conservative padding of the device BVH boxes: box culling never drops a primitive the
      * reference's float32 Hit would accept for any ray that starts within this distance (world units)
-     * of the surface it hits.  0 = derive from the scene and enlarge as needed to cover the camera or
-     * an rt_trace batch (always exact); > 0 = a fixed envelope (use it for scenes much larger than the
-     * distances at which float32 sphere tests are still meaningful). */
+     * of the surface it hits.  0 = derive it from the scene (twice the 90th-percentile extent) and enlarge
+     * it as needed to cover the camera of an rt_render call or the origins of an rt_trace batch: camera rays
+     * and traced batches are then always exact; a SECONDARY ray of rt_render is exact when it starts within
+     * the radius of the surface it hits — from farther away (e.g. off a huge ground sphere, 100 units out) a
+     * hit that exists only through the rounding noise of the reference's float32 discriminant (a geometric
+     * miss by up to 20 u |o-c|^2 / 2r) can be culled.  > 0 = a fixed envelope (use it for scenes much larger
+     * than the distances at which float32 sphere tests are still meaningful; measured
+     * agreement beyond the envelope: profiles/r02j_c4_parity_by_distance.txt). */
     float ray_origin_radius;
     /* Quads (Quad/Box, hittables.go:138-216).  Object IDs: the position of a
      * hittable in World.hittables (hittables.go:48-53), which World.Hit breaks exact ties by.  When

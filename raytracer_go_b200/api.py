@@ -449,15 +449,21 @@ def render_checkpointed(data, cam, path, seed=scenes.RENDER_SEED, chunk_spp=64, 
     the running FP32 sums and the sample cursor are written to `path` (.npz, replaced atomically).  A call that
     finds a checkpoint of the same frame continues at its cursor, so an interrupted render followed by a
     resumed one adds the same chunk sums in the same order as an uninterrupted one: bit-identical images.
+    "The same frame" = same image shape, seed, spp, chunk size, camera bytes, scene bytes (SceneData.sha256 over
+    spheres, quads, materials, textures, Perlin tables and texels) and library ABI version; anything else in the
+    file is ignored and the render starts over.
     `stop_after` = number of chunks to render in this call (to interrupt deliberately).
     Returns (rgb or None while unfinished, sums, samples done)."""
     import os
     shape = (cam.height, cam.width, 3)
     done, acc = 0, np.zeros(shape, np.float32)
+    scene_sha, abi_version = data.sha256(), int(abi.RT_B200_ABI_VERSION)
     if os.path.exists(path):
         with np.load(path) as z:
             if (tuple(z["shape"]) == shape and int(z["seed"]) == seed and int(z["spp"]) == cam.spp
-                    and int(z["chunk_spp"]) == chunk_spp and bytes(z["camera"].tobytes()) == bytes(cam)):
+                    and int(z["chunk_spp"]) == chunk_spp and bytes(z["camera"].tobytes()) == bytes(cam)
+                    and "scene_sha" in z.files and str(z["scene_sha"]) == scene_sha
+                    and int(z["abi_version"]) == abi_version):
                 done, acc = int(z["done"]), z["acc"].astype(np.float32)
     chunks = 0
     with Scene(data, device) as sc:
@@ -469,7 +475,7 @@ def render_checkpointed(data, cam, path, seed=scenes.RENDER_SEED, chunk_spp=64, 
             chunks += 1
             tmp = path + ".tmp.npz"
             np.savez(tmp, acc=acc, done=done, shape=np.array(shape), seed=seed, spp=cam.spp, chunk_spp=chunk_spp,
-                     camera=np.frombuffer(bytes(cam), np.uint8))
+                     camera=np.frombuffer(bytes(cam), np.uint8), scene_sha=scene_sha, abi_version=abi_version)
             os.replace(tmp, path)
     return (resolve_host(acc, cam.spp) if done >= cam.spp else None), acc, done
 

@@ -34,6 +34,7 @@ import (
 	"image"
 	"image/png"
 	"io"
+	"runtime"
 	"strconv"
 	"strings"
 	"unsafe"
@@ -58,7 +59,11 @@ type B200Options struct {
 type b200Flat struct {
 	spheres   []C.rt_sphere
 	quads     []C.rt_quad
-	sphereIDs []C.uint32_t // object ID = first-seen position in the walk (World.hittables order)
+	// Object ID = first-seen position in the walk.  For a *World that is World.hittables order — the order
+	// World.Hit (hittables.go:55-72) breaks exact ties in.  For a *BVH (what main.go passes) the walk is left-then-
+	// right through NewBVH's random-axis tree (bvh.go:147), so IDs follow that run's leaf order: the reference's own
+	// BVH.Hit also resolves an exact tie towards the left subtree (bvh.go:235), i.e. in the same order.
+	sphereIDs []C.uint32_t
 	quadIDs   []C.uint32_t
 	materials []C.rt_material
 	textures  []C.rt_texture
@@ -70,7 +75,12 @@ type b200Flat struct {
 	seenQuads map[quadKey]bool
 }
 
-type quadKey struct{ Q, u, v Vec3 }
+// A Quad is stored by value, so identity is its geometry AND its material: two coincident quads with different
+// materials are two hittables.  (Material is an interface holding a pointer or a comparable struct: valid map key.)
+type quadKey struct {
+	Q, u, v  Vec3
+	material Material
+}
 
 func (f *b200Flat) texture(t Texture) (uint32, error) {
 	if i, ok := f.texIndex[t]; ok {
@@ -195,7 +205,7 @@ func (f *b200Flat) walk(h Hittable) error {
 	case Quad: // hittables.go:138-147 (stored by value: NewQuad returns Quad, main.go:152)
 		// a value type cannot be de-duplicated by pointer; a Quad reaches the walk once unless it is
 		// the only element of a one-element BVH node (bvh.go:162-165), where left == right
-		k := quadKey{hh.Q, hh.u, hh.v}
+		k := quadKey{hh.Q, hh.u, hh.v, hh.material}
 		if f.seenQuads[k] {
 			return nil
 		}
@@ -225,8 +235,15 @@ func cArray[T any](s []T) (unsafe.Pointer, func()) {
 	return p, func() { C.free(p) }
 }
 
-func lastB200Error(code C.int) error {
-	return fmt.Errorf("b200: %s (rt_status %d)", C.GoString(C.rt_last_error()), int(code))
+// rt_last_error() is thread-local in the library, and a goroutine may migrate between OS threads from one cgo call
+// to the next: callB200 pins the goroutine for the failing call AND the fetch of its message.
+func callB200(call func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := call(); rc != C.RT_OK {
+		return fmt.Errorf("b200: %s (rt_status %d)", C.GoString(C.rt_last_error()), int(rc))
+	}
+	return nil
 }
 
 // RenderB200 has the signature and the output of Render (camera.go:180).
@@ -320,18 +337,22 @@ func (c *Camera) RenderB200(world Hittable, writer io.Writer, opt ...B200Options
 		if o.TileSplit {
 			ropts.flags = C.RT_FLAG_TILE_SPLIT
 		}
-		if rc := C.rt_render_multi(&desc, &cam, &ropts, &devs[0], C.int32_t(len(devs)),
-			(*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil); rc != C.RT_OK {
-			return lastB200Error(rc)
+		if err := callB200(func() C.int {
+			return C.rt_render_multi(&desc, &cam, &ropts, &devs[0], C.int32_t(len(devs)),
+				(*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil)
+		}); err != nil {
+			return err
 		}
 	} else {
 		var scene *C.rt_scene
-		if rc := C.rt_scene_create(&desc, C.int(o.Device), &scene); rc != C.RT_OK {
-			return lastB200Error(rc)
+		if err := callB200(func() C.int { return C.rt_scene_create(&desc, C.int(o.Device), &scene) }); err != nil {
+			return err
 		}
 		defer C.rt_scene_destroy(scene)
-		if rc := C.rt_render(scene, &cam, &ropts, (*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil); rc != C.RT_OK {
-			return lastB200Error(rc)
+		if err := callB200(func() C.int {
+			return C.rt_render(scene, &cam, &ropts, (*C.uint8_t)(unsafe.Pointer(&rgb[0])), nil, nil)
+		}); err != nil {
+			return err
 		}
 	}
 

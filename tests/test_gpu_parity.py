@@ -513,6 +513,11 @@ def test_checkpointed_render_resumes_bit_identically(gpu, random_scene, tmp_path
     assert np.array_equal(api.resolve_host(acc, cam.spp), rgb)                 # same arithmetic as the kernel
     assert np.allclose(acc_full, acc, rtol=2e-5, atol=1e-5)                    # chunk sums vs one running sum
     assert (np.abs(full.astype(int) - rgb.astype(int)) <= 1).all()
+    # a checkpoint left by ANOTHER scene under the same camera is not continued: the render starts over
+    other = scenes.random_scene(seed=scenes.SCENE_SEED_RANDOM + 1)
+    api.render_checkpointed(other, cam, str(tmp_path / "c.npz"), SEED, chunk_spp=8, stop_after=2)
+    mixed, acc_mixed, done = api.render_checkpointed(random_scene, cam, str(tmp_path / "c.npz"), SEED, chunk_spp=8)
+    assert done == 37 and np.array_equal(acc_mixed.view(np.uint32), acc_full.view(np.uint32)) and np.array_equal(mixed, full)
 
 
 def test_two_live_scenes_of_different_size_render_alternately(gpu, orc, random_scene):
