@@ -15,7 +15,7 @@
 // contraction off, x86-64 SSE float32 + - * / sqrt round exactly like Go on amd64 (go.mod:3,
 // GOAMD64=v1 has no FMA), so every float32 expression below keeps the reference's operation
 // order.  The RNG is NOT the reference's (math/rand, clock-seeded, camera.go:170): it is a
-// counter-based Philox4x32-10 keyed by (seed; pixel, sample, block) — the published Random123
+// counter-based Philox4x32-7 keyed by (seed; pixel, sample, block) — the published Random123
 // algorithm (Salmon et al., SC'11) — consumed in whole blocks (layout at `struct Rng`) so that
 // oracle and device draw identical values.
 
@@ -102,13 +102,16 @@ inline V3 refract(V3 uv, V3 n, float eta) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Random123).  Stream of one path: counter (pixel, sample, block, 0),
-// key (seed_lo, seed_hi); the four words of a block are consumed in order.
+// Philox4x32-R (Random123).  Stream of one path: counter (pixel, sample, block, 0),
+// key (seed_lo, seed_hi); the four words of a block are consumed in order.  The render streams use
+// g_philox_rounds = 7 (the fewest rounds Random123 reports as Crush-resistant; csrc/rt_rng.h says why);
+// orc_set_philox_rounds(10) switches to Random123's default (the committed converged frame was drawn with it).
 // ---------------------------------------------------------------------------------------------
-inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+int g_philox_rounds = 7;
+inline void philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -152,7 +155,7 @@ struct Rng {
             return b;
         }
         uint32_t w[4];
-        philox4x32_10(ctr, key, w);
+        philox4x32(ctr, key, w, g_philox_rounds);
         ctr[2]++;
         Block b;
         for (int i = 0; i < 4; i++) b.u[i] = (float)(w[i] >> 8) * (1.0f / 16777216.0f);
@@ -827,7 +830,14 @@ int orc_camera_from_options(const rt_camera_options *o, rt_camera *out) {
     return 0;
 }
 
-void orc_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { philox4x32_10(ctr, key, out); }
+void orc_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { philox4x32(ctr, key, out, 10); }
+void orc_philox4x32(const uint32_t *ctr, const uint32_t *key, int rounds, uint32_t *out) { philox4x32(ctr, key, out, rounds); }
+// Rounds of the render streams (7 by default, as the device); returns the previous value.
+int orc_set_philox_rounds(int rounds) {
+    const int prev = g_philox_rounds;
+    if (rounds >= 1 && rounds <= 16) g_philox_rounds = rounds;
+    return prev;
+}
 
 // The uniforms of the first ceil(n/4) blocks of the stream of (seed, pixel, sample).
 void orc_rng_floats(uint64_t seed, uint32_t pixel, uint32_t sample, int n, float *out) {

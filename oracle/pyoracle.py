@@ -43,6 +43,9 @@ def lib():
         L.orc_camera_from_options.argtypes = [C.POINTER(abi.rt_camera_options), C.POINTER(abi.rt_camera)]
         L.orc_philox4x32_10.argtypes = [C.c_void_p] * 3
         L.orc_philox4x32_10.restype = None
+        L.orc_philox4x32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_philox4x32.restype = None
+        L.orc_set_philox_rounds.argtypes = [C.c_int]
         L.orc_rng_floats.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
         L.orc_rng_floats.restype = None
         L.orc_trace.argtypes = [C.POINTER(abi.rt_scene_desc), C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
@@ -99,12 +102,21 @@ def camera_from_options(opts):
     return cam
 
 
-def philox(ctr, key):
+STREAM_ROUNDS = 7  # Philox rounds of the render streams (csrc/rt_rng.h: RT_PHILOX_ROUNDS)
+
+
+def philox(ctr, key, rounds=10):
+    """Philox4x32 with `rounds` rounds (10 = Random123's default; the render streams use STREAM_ROUNDS)."""
     c = np.ascontiguousarray(ctr, np.uint32)
     k = np.ascontiguousarray(key, np.uint32)
     out = np.zeros(4, np.uint32)
-    lib().orc_philox4x32_10(_p(c), _p(k), _p(out))
+    lib().orc_philox4x32(_p(c), _p(k), rounds, _p(out))
     return out
+
+
+def set_philox_rounds(rounds):
+    """Rounds of the oracle's render streams; returns the previous value."""
+    return int(lib().orc_set_philox_rounds(rounds))
 
 
 def rng_floats(seed, pixel, sample, n):

@@ -1,16 +1,16 @@
-// rt_rng.h — counter-based Philox4x32-10 stream, one per (pixel, sample) path.
+// rt_rng.h — counter-based Philox4x32-7 stream, one per (pixel, sample) path.
 //
 // The reference draws from clock-seeded math/rand generators (camera.go:170-171, materials.go:103);
 // that stream is not reproducible and not part of any contract.  Here the stream of a path is the
 // sequence of BLOCKS
-//   block b = Philox4x32-10( counter = (pixel, sample, b, 0), key = (seed_lo, seed_hi) ),  b = 0,1,2,...
+//   block b = Philox4x32-7( counter = (pixel, sample, b, 0), key = (seed_lo, seed_hi) ),  b = 0,1,2,...
 // each giving four uniforms  Float32() = (word >> 8) * 2^-24  in [0,1), and every consumer takes
 // whole blocks (a partly used block is dropped):
 //   Camera.GetRay          one block = (dx, dy, disk.x, disk.y); while the disk pair is rejected
 //                          (vec3.go:203-210) another block = two more candidate pairs, tried in order
 //   unit-sphere rejection  one block per trial = (x, y, z, unused)      (vec3.go:182-190)
 //   Dielectric.Scatter     one block, first word = the uniform of materials.go:103
-// Whole-block consumption keeps the ten Philox rounds at warp-convergent program points (every lane
+// Whole-block consumption keeps the Philox rounds at warp-convergent program points (every lane
 // still in a rejection loop generates together) instead of inside a per-lane "buffer empty" branch.
 // Any (pixel, sample) can be generated on any GPU in any order, so sample-split / tile-split renders
 // draw exactly the samples of the single-GPU render.
@@ -24,11 +24,21 @@ struct RngBlock {
     uint32_t w0, w1, w2, w3; // the words themselves (for the fused mappings below)
 };
 
-// The ten round keys (k0 + r*W0, k1 + r*W1) depend on the seed only.  On the device they live in
+// Rounds: Random123 (Salmon et al., SC'11, table 2) lists Philox4x32 with 7 rounds as the fastest variant that passes
+// TestU01's BigCrush ("Crush-resistant"); 10 rounds, its default, add a safety margin that a Monte-Carlo integrator
+// of a 405 M-sample frame does not need.  The rejection samplers make the generator 18 % of the frame's instructions
+// (profiles/r02p_*_by_line.txt), 40 instructions per block at 10 rounds; 7 rounds measured +4.1 % on C2, +3.6 % on
+// C3, +6.0 % on the Cornell box (profiles/r02q).  Both round counts are pinned by Random123's known-answer vectors
+// (tests/test_oracle_kat.py); the oracle draws the same 7-round stream, and the converged-image test compares the
+// device with an oracle frame drawn from the 10-round stream.  -DRT_PHILOX_ROUNDS=10 builds the other variant.
+//
+// The round keys (k0 + r*W0, k1 + r*W1) depend on the seed only.  On the device they live in
 // constant memory (philox_round_keys() fills the array, the host uploads it before a launch), so
 // the xor of a round takes its key as a constant-bank operand: no key registers, no 18 key adds
 // per block.  The host build (tests/hostsim) keeps them in a thread-local array.
-#define RT_PHILOX_ROUNDS 10
+#ifndef RT_PHILOX_ROUNDS
+#define RT_PHILOX_ROUNDS 7
+#endif
 RT_HD void philox_round_keys(uint64_t seed, uint32_t *rk) {
     uint32_t q0 = (uint32_t)seed, q1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < RT_PHILOX_ROUNDS; r++) {

@@ -1,7 +1,8 @@
-"""Vectorised Philox4x32-10 (Random123; Salmon et al., SC'11) in numpy.
+"""Vectorised Philox4x32 (Random123; Salmon et al., SC'11) in numpy.
 
 Used only to synthesise deterministic scenes (the reference seeds its scene RNG from the clock,
-main.go:246).  The render-time streams live in the CUDA kernels (csrc/philox.cuh).
+main.go:246), with Random123's default 10 rounds.  The render-time streams live in the CUDA kernels
+(csrc/rt_rng.h) and use 7 rounds; the scenes do not depend on that choice.
 """
 import numpy as np
 
@@ -13,12 +14,12 @@ _MASK = np.uint64(0xFFFFFFFF)
 _S32 = np.uint64(32)
 
 
-def philox4x32_10(ctr, key):
+def philox4x32_10(ctr, key, rounds=10):
     """ctr: (..., 4) uint32, key: (2,) uint32-like -> (..., 4) uint32."""
     ctr = np.asarray(ctr, dtype=np.uint32)
     c0, c1, c2, c3 = (ctr[..., i].astype(np.uint64) for i in range(4))
     k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = _M0 * c0
         p1 = _M1 * c2
         n0 = (p1 >> _S32) ^ c1 ^ np.uint64(k0)

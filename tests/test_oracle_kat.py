@@ -24,16 +24,22 @@ def one_sphere(c=(0, 0, -1), r=0.5, n=1):
 
 
 def test_philox_random123_vectors(orc):
-    """Random123 kat_vectors for philox4x32-10."""
+    """Random123 kat_vectors for philox4x32 with 10 rounds (its default; the scene generators use it) and with 7
+    rounds (the render streams, csrc/rt_rng.h): zero, all-ones and pi-digit counters / keys."""
+    zero, ones = ([0, 0, 0, 0], [0, 0]), ([0xffffffff] * 4, [0xffffffff] * 2)
+    pi = ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])
     kats = [
-        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
-        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
-        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
-         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+        (10, *zero, [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        (10, *ones, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        (10, *pi, [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+        (7, *zero, [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]),
+        (7, *ones, [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]),
+        (7, *pi, [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]),
     ]
-    for ctr, key, want in kats:
-        assert orc.philox(ctr, key).tolist() == want
-        assert philox.philox4x32_10(np.array(ctr, np.uint32), key).tolist() == want
+    for rounds, ctr, key, want in kats:
+        assert orc.philox(ctr, key, rounds).tolist() == want
+        assert philox.philox4x32_10(np.array(ctr, np.uint32), key, rounds).tolist() == want
+    assert orc.STREAM_ROUNDS == 7
 
 
 def test_rng_stream_layout(orc):
@@ -42,7 +48,7 @@ def test_rng_stream_layout(orc):
     f = orc.rng_floats(seed, 77, 5, 10)
     want = []
     for blk in range(3):
-        w = orc.philox([77, 5, blk, 0], [seed & 0xFFFFFFFF, seed >> 32])
+        w = orc.philox([77, 5, blk, 0], [seed & 0xFFFFFFFF, seed >> 32], orc.STREAM_ROUNDS)
         want += [F(int(x) >> 8) * F(2.0 ** -24) for x in w]
     assert f.tolist() == [float(x) for x in want[:10]]
     assert (f >= 0).all() and (f < 1).all()
