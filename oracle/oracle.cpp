@@ -9,7 +9,10 @@
 // PARITY PIN STATUS — "parity unpinned" by the reference: the reference ships no tests, golden
 // vectors or fixtures and Go is not installed here, so this restatement is
 // pinned only by the hand-derived known-answer tests of SURVEY.md §4 (tests/test_oracle_kat.py)
-// and by being an independent second implementation next to the device code.
+// and by being an independent second implementation next to the device code.  What pins it wherever
+// Go exists is committed: raytracer_go_b200/go/parity_dump_test.go evaluates tests/golden/pin_inputs.json with
+// the reference's own functions, scripts/pin_from_go.sh runs it, tests/test_pin_from_go.py compares (the fed
+// entry points orc_scatter_fed / orc_get_color_fed / orc_get_ray_fed below exist for that comparison).
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math (see oracle/Makefile).  With
 // contraction off, x86-64 SSE float32 + - * / sqrt round exactly like Go on amd64 (go.mod:3,

@@ -957,7 +957,10 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
         stats->samples = (uint64_t)n_pix * (uint64_t)spp;
         stats->rays = h[0], stats->hits = h[1], stats->box_tests = h[2], stats->sphere_tests = h[3];
         stats->survivors = h[4];
-        stats->work_bytes = 32ull * stats->samples + 96ull * h[4] + 24ull * (uint64_t)n_pix * n_passes_total;
+        // HBM bytes of the call's work buffers: a 16-byte radiance record written and read per path, a 48-byte queue
+        // entry written and read per survivor, the accumulator read + written per pass, the candidate lists written once
+        stats->work_bytes = 32ull * stats->samples + 96ull * h[4] + 24ull * (uint64_t)n_pix * n_passes_total +
+                            (use_lists ? (uint64_t)RT_LIST_WORDS * 4ull * n_pix : 0ull);
         float total = 0;
         for (size_t e = 2; e < n_ev; e += 2) {
             float ms = 0;
