@@ -336,13 +336,14 @@ __global__ void bd_slots(BdParams p) {
 __global__ void bd_depth(BdParams p) {
     const int nn = (int)(p.n - p.st->n_large);
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nn) return;
-    unsigned int depth = p.st->n_large;
-    if (nn >= 2)
-        for (int node = p.parent[p.n + (uint32_t)j]; node >= 0; node = p.parent[node]) depth += p.live[node];
-    // warp maximum, one atomic per warp
-    for (int off = 16; off > 0; off >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, off));
-    if ((threadIdx.x & 31) == 0) atomicMax(&p.st->max_depth, depth);
+    unsigned int depth = 0; // lanes past the end stay in the warp for the reduction below
+    if (j < nn) {
+        depth = p.st->n_large;
+        if (nn >= 2)
+            for (int node = p.parent[p.n + (uint32_t)j]; node >= 0; node = p.parent[node]) depth += p.live[node];
+    }
+    depth = __reduce_max_sync(0xffffffffu, depth); // one atomic per warp
+    if ((threadIdx.x & 31) == 0 && depth) atomicMax(&p.st->max_depth, depth);
 }
 
 // pack_materials (bvh_build.cpp) on the device: the texture folded into each 32-byte material record (rt_shade.h)
