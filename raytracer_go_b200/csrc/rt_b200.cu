@@ -1176,8 +1176,8 @@ static int rt_render_multi_impl(const rt_scene_desc *desc, const rt_camera *came
     // the root's buffers every device writes into or reads from, allocated before the device threads start
     const int root = devs[0];
     Workspace &w0 = g_ws[root];
-    RC(select_device(root));
-    enable_peer_access(devs);
+    enable_peer_access(devs); // (leaves some other device current)
+    RC(select_device(root));  // the buffers below belong to the root
     RC(ws_reserve(w0.rgb, w0.rgb_cap, (size_t)n_pix * 3));
     RC(ws_reserve(w0.h_rgb, w0.h_rgb_cap, (size_t)n_pix * 3, true));
     if (accum_out) RC(ws_reserve(w0.h_accum, w0.h_accum_cap, n_acc, true));
