@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
             if (FIRST && p.lists != nullptr) { // the candidates of this path's pixel (camera rays only)
                 list = p.lists + (size_t)fast_div(idx, p.div_spp) * RT_LIST_WORDS;
                 n_list = list[0];
+                RT_DBG(n_list == RT_LIST_OVERFLOW || n_list < RT_LIST_WORDS, RT_DBG_LEAF);
             }
             if (FIRST && n_list != RT_LIST_OVERFLOW)
                 trace_candidates<COUNT, QUADS>(list + 1, n_list, sph, meta, quads, o, d, 0.001f, INFINITY, h, &wc);

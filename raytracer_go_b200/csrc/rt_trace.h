@@ -387,6 +387,7 @@ RT_HD void trace_candidates(const uint32_t *__restrict__ list, uint32_t n, const
     if (COUNT) wc->sphere_tests += n;
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t hs = list[k];
+        RT_DBG((hs & ~RT_HIT_QUAD) < ((hs & RT_HIT_QUAD) ? RT_DBG_B(n_quad_slots) : RT_DBG_B(n_slots)), RT_DBG_LEAF);
         float t;
         if (QUADS && (hs & RT_HIT_QUAD)) {
             if (!quad_candidate(quads + (size_t)RT_QUAD_F4 * (hs & ~RT_HIT_QUAD), o, d, tmin, tbest, t)) continue;
