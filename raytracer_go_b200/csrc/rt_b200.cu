@@ -20,6 +20,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -254,6 +255,40 @@ static int select_device(int device) {
     return RT_OK;
 }
 
+// ok(i) for every i in [0, n): RT_OK, or the status (and message) of the FIRST element that fails.  Arrays of a million
+// elements (one material and texture per sphere in the stress scene) are checked on up to 8 threads — 7 ms of a 119 ms
+// C4 frame otherwise; the workers only find the index, the caller's thread repeats that one check for the message.
+template <class F>
+static int check_all(uint64_t n, F ok) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned parts = n >= (1u << 17) ? std::min(8u, hw) : 1u;
+    if (parts <= 1) {
+        for (uint64_t i = 0; i < n; i++) RC(ok(i));
+        return RT_OK;
+    }
+    std::vector<uint64_t> bad(parts, n);
+    const uint64_t step = (n + parts - 1) / parts;
+    auto scan = [&](unsigned c) {
+        for (uint64_t i = (uint64_t)c * step, e = std::min(n, i + step); i < e; i++)
+            if (ok(i) != RT_OK) {
+                bad[c] = i;
+                return;
+            }
+    };
+    std::vector<std::thread> th;
+    for (unsigned c = 1; c < parts; c++) {
+        try {
+            th.emplace_back(scan, c);
+        } catch (const std::system_error &) {
+            scan(c);
+        }
+    }
+    scan(0);
+    for (auto &t : th) t.join();
+    const uint64_t first = *std::min_element(bad.begin(), bad.end());
+    return first < n ? ok(first) : RT_OK;
+}
+
 static int validate_desc(const rt_scene_desc *d) {
     if (!d) return fail(RT_ERR_INVALID_ARGUMENT, "scene desc is null");
     if (d->abi_version != RT_B200_ABI_VERSION)
@@ -267,35 +302,43 @@ static int validate_desc(const rt_scene_desc *d) {
                     (unsigned long long)d->n_quads);
     if ((d->sphere_ids != nullptr) != (d->quad_ids != nullptr) && d->n_spheres && d->n_quads)
         return fail(RT_ERR_INVALID_ARGUMENT, "sphere_ids and quad_ids must be given together");
-    for (uint64_t i = 0; i < d->n_quads; i++) {
+    auto quad_ok = [&](uint64_t i) -> int {
         const rt_quad &q = d->quads[i];
         if (q.material >= d->n_materials)
             return fail(RT_ERR_INVALID_ARGUMENT, "quad %llu: material %u out of range", (unsigned long long)i, q.material);
         for (int k = 0; k < 3; k++)
             if (!std::isfinite(q.q[k]) || !std::isfinite(q.u[k]) || !std::isfinite(q.v[k]))
                 return fail(RT_ERR_INVALID_ARGUMENT, "quad %llu: non-finite geometry", (unsigned long long)i);
-    }
-    for (uint64_t i = 0; i < d->n_spheres; i++) {
+        return RT_OK;
+    };
+    auto sphere_ok = [&](uint64_t i) -> int {
         const rt_sphere &s = d->spheres[i];
         if (s.material >= d->n_materials)
             return fail(RT_ERR_INVALID_ARGUMENT, "sphere %llu: material %u out of range", (unsigned long long)i, s.material);
         if (!std::isfinite(s.cx) || !std::isfinite(s.cy) || !std::isfinite(s.cz) || !std::isfinite(s.r))
             return fail(RT_ERR_INVALID_ARGUMENT, "sphere %llu: non-finite geometry", (unsigned long long)i);
-    }
-    for (uint32_t i = 0; i < d->n_materials; i++) {
+        return RT_OK;
+    };
+    auto material_ok = [&](uint64_t i) -> int {
         const rt_material &m = d->materials[i];
-        if (m.kind > RT_MAT_DIFFUSE_LIGHT) return fail(RT_ERR_UNSUPPORTED, "material %u: unknown kind %u", i, m.kind);
+        if (m.kind > RT_MAT_DIFFUSE_LIGHT) return fail(RT_ERR_UNSUPPORTED, "material %u: unknown kind %u", (uint32_t)i, m.kind);
         if ((m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT) && m.texture >= d->n_textures)
-            return fail(RT_ERR_INVALID_ARGUMENT, "material %u: texture %u out of range", i, m.texture);
-    }
-    for (uint32_t i = 0; i < d->n_textures; i++) {
+            return fail(RT_ERR_INVALID_ARGUMENT, "material %u: texture %u out of range", (uint32_t)i, m.texture);
+        return RT_OK;
+    };
+    auto texture_ok = [&](uint64_t i) -> int {
         const rt_texture &t = d->textures[i];
-        if (t.kind > RT_TEX_NOISE) return fail(RT_ERR_UNSUPPORTED, "texture %u: unknown kind %u", i, t.kind);
+        if (t.kind > RT_TEX_NOISE) return fail(RT_ERR_UNSUPPORTED, "texture %u: unknown kind %u", (uint32_t)i, t.kind);
         if (t.kind == RT_TEX_NOISE && t.image >= d->n_perlins)
-            return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: perlin table %u out of range", i, t.image);
+            return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: perlin table %u out of range", (uint32_t)i, t.image);
         if (t.kind == RT_TEX_IMAGE && t.image >= d->n_images)
-            return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: image %u out of range", i, t.image);
-    }
+            return fail(RT_ERR_INVALID_ARGUMENT, "texture %u: image %u out of range", (uint32_t)i, t.image);
+        return RT_OK;
+    };
+    RC(check_all(d->n_quads, quad_ok));
+    RC(check_all(d->n_spheres, sphere_ok));
+    RC(check_all(d->n_materials, material_ok));
+    RC(check_all(d->n_textures, texture_ok));
     for (uint32_t i = 0; i < d->n_images; i++)
         if (d->images[i].w > 0 && d->images[i].h > 0 && !d->images[i].rgb16)
             return fail(RT_ERR_INVALID_ARGUMENT, "image %u: null texels", i);

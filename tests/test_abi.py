@@ -105,6 +105,32 @@ def test_non_finite_geometry_is_rejected(rtlib):
     assert rc in (abi.RT_ERR_INVALID_ARGUMENT, abi.RT_ERR_NO_DEVICE)   # the id check needs the device selected first
 
 
+def test_large_scene_validation_reports_the_first_bad_element(rtlib):
+    """Arrays of >= 131 072 elements are validated on several threads; the error is still the FIRST bad element's."""
+    n = 300_000
+    sph = np.zeros(n, scenes.SPHERE_DT)
+    sph["r"] = 0.2
+    sph["cx"] = np.arange(n, dtype=np.float32)
+    mats = np.zeros(1, scenes.MATERIAL_DT)
+    tex = np.zeros(1, scenes.TEXTURE_DT)
+    sph["material"][250_001] = 5          # out of range, in the last thread's share
+    sph["cy"][140_000] = np.nan           # non-finite, earlier: this is the one to report
+    desc, keep = scenes.SceneData(sph, mats, tex).to_desc()
+    h = C.c_void_p()
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_INVALID_ARGUMENT
+    assert rtlib.rt_last_error() == b"sphere 140000: non-finite geometry"
+    sph["cy"][140_000] = 0.0
+    desc, keep = scenes.SceneData(sph, mats, tex).to_desc()
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_INVALID_ARGUMENT
+    assert rtlib.rt_last_error() == b"sphere 250001: material 5 out of range"
+    many = np.zeros(200_000, scenes.MATERIAL_DT)
+    many["kind"][199_999] = 77
+    sph["material"][250_001] = 0
+    desc, keep = scenes.SceneData(sph, many, tex).to_desc()
+    assert rtlib.rt_scene_create(C.byref(desc), 0, C.byref(h)) == abi.RT_ERR_UNSUPPORTED
+    assert rtlib.rt_last_error() == b"material 199999: unknown kind 77"
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the
     contract's keys on rank 0, nothing and exit 0 on the other ranks of a torchrun launch."""

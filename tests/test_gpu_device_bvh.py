@@ -105,3 +105,22 @@ def test_c4_device_build_is_the_default_and_equals_the_host_build(gpu, orc, monk
     same = (acc.view(np.uint32) == hacc.view(np.uint32)).all(-1)
     assert same.mean() > 0.995, f"{(~same).sum()} pixels differ"
     assert abs(int(st.rays) - int(hst.rays)) < 1e-3 * hst.rays
+
+
+def test_large_scene_through_render_multi(gpu, monkeypatch):
+    """rt_render_multi on a scene every device builds for itself (device builder): the raw arrays are uploaded once to
+    devices[0] and copied to the others over NVLink (DeviceStaging).  Tile-split is bitwise the single-GPU render,
+    sample-split equal up to the FP32 summation order; with one GPU the call degenerates to rt_render."""
+    monkeypatch.delenv("RT_B200_DEVICE_BVH", raising=False)
+    scene = scenes.stress_scene(130)          # 67 600 cells -> above the device builder's 50 000-sphere threshold
+    assert len(scene.spheres) > 60_000
+    cam = api.camera_from_options(scenes.camera_options(320, 6, look_from=(52, 24, 12)))
+    with api.Scene(scene) as sc:
+        assert sc.bvh_info().built_on_device == 1
+        rgb, acc, st = sc.render(cam, SEED, want_accum=True)
+    devs = list(range(min(gpu, 4)))
+    trgb, tacc, tst = api.render_multi(scene, cam, devs, SEED, want_accum=True, tile_split=True)
+    assert np.array_equal(trgb, rgb) and np.array_equal(tacc.view(np.uint32), acc.view(np.uint32)) and tst.samples == st.samples
+    srgb, sacc, sst = api.render_multi(scene, cam, devs, SEED, want_accum=True)
+    assert sst.rays == st.rays and np.allclose(sacc, acc, rtol=2e-5, atol=1e-5)
+    assert (np.abs(srgb.astype(int) - rgb.astype(int)) <= 1).all()
