@@ -380,9 +380,8 @@ def test_leaf_start_on_quads_and_fuzz_scenes(hs, orc):
 
 
 def hs_pixel_candidates(hs, scene, opts, n_pixels, stride, spp, begin=0, cap=15):
-    cam = api.camera_from_options(opts) if False else None  # (the camera comes from the oracle: no GPU library needed)
     from oracle import pyoracle as orc
-    cam = orc.camera_from_options(opts)
+    cam = orc.camera_from_options(opts)  # (from the oracle: this test needs no GPU library)
     desc, keep = scene.to_desc()
     out = (C.c_double * 6)()
     rc = hs.hs_pixel_candidates(C.byref(desc), C.byref(cam), C.c_uint64(123), C.c_int64(begin), C.c_int64(n_pixels),
