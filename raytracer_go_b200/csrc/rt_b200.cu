@@ -923,9 +923,10 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     Workspace &ws = g_ws[s->device];
     rc = ws_reserve(ws.samples, ws.samples_cap, need);
     if (rc == RT_OK && s->use_split) rc = ws_reserve(ws.queue, ws.queue_cap, (s->n_stages > 1 ? 6 : 3) * need);
-    // per-pixel candidate lists for the camera rays (two-stage mode): worth their one walk per pixel from a few
-    // samples per pixel on; RT_B200_PIXEL_LISTS=0 turns them off (A/B)
-    const bool use_lists = s->use_split && s->n_prims > 0 && spp >= env_int("RT_B200_PIXEL_LISTS_MIN_SPP", 4) &&
+    // per-pixel candidate lists for the camera rays (two-stage mode).  The walk costs 0.18 ms per C2 frame and saves
+    // 0.012 ms per sample per pixel in the primary stage: worth it from ~15 samples per pixel on (at C1's 10 spp the
+    // lists cost 2 %, profiles/r02l).  RT_B200_PIXEL_LISTS=0 turns them off (A/B)
+    const bool use_lists = s->use_split && s->n_prims > 0 && spp >= env_int("RT_B200_PIXEL_LISTS_MIN_SPP", 16) &&
                            env_int("RT_B200_PIXEL_LISTS", 1) != 0;
     if (rc == RT_OK && use_lists) rc = ws_reserve(ws.lists, ws.lists_cap, (size_t)pix_tile * RT_LIST_WORDS);
     if (rc != RT_OK) return rc;

@@ -520,6 +520,31 @@ def test_checkpointed_render_resumes_bit_identically(gpu, random_scene, tmp_path
     assert done == 37 and np.array_equal(acc_mixed.view(np.uint32), acc_full.view(np.uint32)) and np.array_equal(mixed, full)
 
 
+def test_candidate_lists_on_off_and_default_are_bit_identical(gpu, orc, random_scene, monkeypatch):
+    """The per-pixel candidate lists (rt_kernels.cuh: pixel_candidates_kernel) never change a result: the same frame
+    with the lists forced on, switched off, and under the library's default threshold (16 spp: off at 6 spp, on at 20)
+    is bit-identical, and equal to the oracle's."""
+    def frame(spp, **env):
+        for k in ("RT_B200_PIXEL_LISTS", "RT_B200_PIXEL_LISTS_MIN_SPP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with api.Scene(random_scene) as sc:
+            rgb, acc, st = sc.render(_cam(200, spp), SEED, want_accum=True)
+        return rgb, acc, st
+    for spp in (6, 20):
+        on = frame(spp, RT_B200_PIXEL_LISTS_MIN_SPP="1")
+        off = frame(spp, RT_B200_PIXEL_LISTS="0")
+        dflt = frame(spp)
+        assert on[2].kernel_launches == off[2].kernel_launches + 1          # the one walk per call
+        assert dflt[2].kernel_launches == (on if spp >= 16 else off)[2].kernel_launches
+        for other in (off, dflt):
+            assert np.array_equal(on[1].view(np.uint32), other[1].view(np.uint32)) and np.array_equal(on[0], other[0])
+            assert on[2].rays == other[2].rays
+    rrgb, racc, _ = orc.render(random_scene, _cam(200, 6), SEED, order=orc.ORDER_ITERATIVE)
+    assert np.array_equal(frame(6, RT_B200_PIXEL_LISTS_MIN_SPP="1")[1].view(np.uint32), racc.view(np.uint32))
+
+
 def test_two_live_scenes_of_different_size_render_alternately(gpu, orc, random_scene):
     """Two handles on one device whose shared-memory stagings differ (both above 48 KB would be the failing case
     of a per-handle cudaFuncSetAttribute; the attribute is a per-device high-water mark): renders alternate
