@@ -54,6 +54,27 @@ def test_rng_stream_layout(orc):
     assert (f >= 0).all() and (f < 1).all()
 
 
+def test_seven_round_streams_pass_basic_statistics(orc):
+    """Not a substitute for BigCrush (Random123 reports Philox4x32-7 as Crush-resistant) — a guard against a gross
+    mistake in how the 7-round streams are keyed: uniforms of neighbouring pixels / samples / blocks must look
+    independent.  4-sigma bounds on the mean, a 256-bin chi-square, and correlations along each counter axis."""
+    seed = 0xC0FFEE
+    pix = np.stack([orc.rng_floats(seed, p, 0, 64) for p in range(4096)])          # consecutive pixels, sample 0
+    smp = np.stack([orc.rng_floats(seed, 1234, k, 64) for k in range(4096)])       # one pixel, consecutive samples
+    for u in (pix, smp):
+        n = u.size
+        assert abs(float(u.mean()) - 0.5) < 4 * np.sqrt(1 / 12 / n)
+        hist = np.bincount((u.ravel() * 256).astype(int), minlength=256)
+        chi2 = float(((hist - n / 256) ** 2 / (n / 256)).sum())
+        assert 255 - 5 * np.sqrt(2 * 255) < chi2 < 255 + 5 * np.sqrt(2 * 255)
+        c = u - 0.5
+        bound = 5 / 12 / np.sqrt(c[1:].size)                                        # 5 sigma of a product of two uniforms
+        assert abs(float((c[1:] * c[:-1]).mean())) < bound                          # along the pixel / sample axis
+        assert abs(float((c[:, 1:] * c[:, :-1]).mean())) < bound                    # along the word / block axis
+        assert abs(float((c[:, 4:] * c[:, :-4]).mean())) < bound                    # same word of consecutive blocks
+    assert abs(float(((pix - 0.5) * (smp - 0.5)).mean())) < 5 / 12 / np.sqrt(pix.size)
+
+
 def test_sphere_front_hit(orc):
     """hittables.go:97-126: a=1, halfB=-1, c=0.75, disc=0.25, t=0.5; u=11/24, v=0.5."""
     h = orc.hit_info(one_sphere(), (0, 0, 0), (0, 0, -1))
