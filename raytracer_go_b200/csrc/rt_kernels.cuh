@@ -181,26 +181,49 @@ __device__ __forceinline__ uint32_t image_pixel(const RenderParams &p, uint32_t 
 #define RT_LIST_OVERFLOW 0xFFFFFFFFu
 #define RT_MAX_STAGES 8 /* coherent stage kernels before the megakernel (staged mode) */
 
-// BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
-template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS, bool SPLIT = false>
-__global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_constant__ RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
-    const I2 *meta = p.sc.meta;
-    const uint32_t *chains = p.sc.chains, *sph_chain = p.sc.chains ? p.sc.sph_chain : nullptr, *quad_chain = p.sc.quad_chain;
-    uint32_t *stack_mem = nullptr;
-    if (SMEM) {
-        SmemScene s = stage_scene<RT_PACKED(SMEM, QUADS)>(p.sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta, stack_mem = s.stack;
-        chains = s.chains, sph_chain = s.sph_chain, quad_chain = s.quad_chain;
-    }
-    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
-    Stack stack;
+// The pointers a kernel reads the scene through: global memory, or the CTA's shared-memory copy (stage_scene).
+struct SceneView {
+    const F4 *nodes, *sph, *mats, *quads;
+    const I2 *meta;
+    const uint32_t *chains, *sph_chain, *quad_chain;
+};
+template <bool SMEM, bool QUADS, class Stack, int BLOCK>
+__device__ __forceinline__ SceneView open_scene(const DevScene &sc, unsigned char *smem_raw, Stack &stack) {
+    SceneView v;
+    v.nodes = sc.nodes, v.sph = sc.sph, v.mats = sc.mats, v.quads = sc.quads, v.meta = sc.meta;
+    v.chains = sc.chains, v.sph_chain = sc.chains ? sc.sph_chain : nullptr, v.quad_chain = sc.quad_chain;
     if constexpr (SMEM) {
-        stack.base = stack_mem + threadIdx.x;
+        SmemScene s = stage_scene<RT_PACKED(SMEM, QUADS)>(sc, smem_raw);
+        v.nodes = s.nodes, v.sph = s.sph, v.mats = s.mats, v.quads = s.quads, v.meta = s.meta;
+        v.chains = s.chains, v.sph_chain = s.sph_chain, v.quad_chain = s.quad_chain;
+        stack.base = s.stack + threadIdx.x;
         stack.stride = BLOCK;
     }
+    return v;
+}
 
+// work counters: warp shuffle reduction, one atomic per warp
+template <bool COUNT>
+__device__ __forceinline__ void flush_counters(unsigned long long *stats, unsigned long long n_rays, unsigned long long n_hits,
+                                               const WorkCounters &wc) {
+    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
+#pragma unroll
+    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
+        unsigned long long x = v[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31u) == 0 && x) atomicAdd(stats + q, x);
+    }
+}
+
+// The megakernel's loop: one lane = one (pixel, sample) path at a time, dead lanes regenerate from the warp's chunk of
+// the pass's work items (all paths, or — SPLIT — the survivors queued by the primary stage).
+template <class Stack, bool SMEM, bool COUNT, bool QUADS, bool SPLIT>
+__device__ __forceinline__ void path_loop(const RenderParams &p, const SceneView &sv, Stack &stack, unsigned long long &n_rays,
+                                          unsigned long long &n_hits, WorkCounters &wc) {
+    const F4 *nodes = sv.nodes, *sph = sv.sph, *mats = sv.mats, *quads = sv.quads;
+    const I2 *meta = sv.meta;
+    const uint32_t *chains = sv.chains, *sph_chain = sv.sph_chain, *quad_chain = sv.quad_chain;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t warp_next = 0, warp_end = 0;
@@ -216,9 +239,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
     V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1), rad = v3(0, 0, 0);
     PathRng rng;
     rng.init(0, 0, 0);
-    unsigned long long n_rays = 0, n_hits = 0;
-    WorkCounters wc;
-    wc.box_tests = wc.sphere_tests = 0;
 
     for (;;) {
         // ---- regeneration: dead lanes take the next path indices of the warp's chunk ----
@@ -316,15 +336,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
         }
     }
 
-    // ---- work counters: warp shuffle reduction, one atomic per warp ----
-    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
-#pragma unroll
-    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
-        unsigned long long x = v[q];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0 && x) atomicAdd(p.stats + q, x);
-    }
+}
+
+// BLOCK x MINB resident threads per SM bound the register budget (65536 / (BLOCK * MINB)).
+template <int BLOCK, int MINB, bool SMEM, bool COUNT, bool QUADS, bool SPLIT = false>
+__global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_constant__ RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
+    Stack stack;
+    const SceneView sv = open_scene<SMEM, QUADS, Stack, BLOCK>(p.sc, smem_raw, stack);
+    unsigned long long n_rays = 0, n_hits = 0;
+    WorkCounters wc;
+    wc.box_tests = wc.sphere_tests = 0;
+    path_loop<Stack, SMEM, COUNT, QUADS, SPLIT>(p, sv, stack, n_rays, n_hits, wc);
+    flush_counters<COUNT>(p.stats, n_rays, n_hits, wc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,22 +363,140 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_kernel(const __grid_consta
 // Same functions, same order per path as the one-stage kernel: the image is bit-identical.
 // FIRST = false: the same for a later segment — the rays come from the previous stage's queue (in
 // pixel-neighbour order, all lanes alive) instead of the camera.
+// One round of the primary stage for the calling thread: work item `item` of `n_items` (lanes past the end idle, but
+// take part in the warp- / CTA-wide queue append).  cta_count / cta_base: BLOCK / 32 words of shared memory (global-memory
+// scenes append once per CTA and round, behind two barriers — every thread of the CTA must then call this together).
+template <class Stack, int BLOCK, bool SMEM, bool COUNT, bool QUADS, bool FIRST>
+__device__ __forceinline__ void primary_round(const RenderParams &p, const SceneView &sv, Stack &stack, uint32_t item, uint32_t n_items,
+                                              unsigned long long &n_rays, unsigned long long &n_hits, WorkCounters &wc,
+                                              uint32_t *cta_count, uint32_t *cta_base) {
+    const F4 *nodes = sv.nodes, *sph = sv.sph, *mats = sv.mats, *quads = sv.quads;
+    const I2 *meta = sv.meta;
+    const uint32_t *chains = sv.chains, *sph_chain = sv.sph_chain, *quad_chain = sv.quad_chain;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t idx = item;
+    bool survive = false, carries = false;
+    V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1);
+    uint32_t block = 0, hit_slot = RT_REF_NONE;
+    if (item < n_items) {
+        PathRng rng;
+        V3 rad = v3(0, 0, 0);
+        uint32_t start = RT_REF_NONE;
+        if (FIRST) {
+            const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
+            const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
+            const int j = (int)fast_div(pixel, p.div_width), i = (int)(pixel - (uint32_t)j * p.cam.width);
+            rng.init(p.seed, pixel, p.sample_begin + k);
+            generate_ray(p.cam, rng, i, j, o, d);
+        } else {
+            RT_DBG(item < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
+            const float4 qo = p.in_o[item], qd = p.in_d[item], qt = p.in_t[item];
+            idx = __float_as_uint(qo.w);
+            const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
+            rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
+            rng.block = __float_as_uint(qd.w) & 0x7fffffffu;
+            o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z), thr = v3(qt.x, qt.y, qt.z);
+            start = chain_of_slot(sph_chain, quad_chain, __float_as_uint(qt.w));
+            if (__float_as_uint(qd.w) & 0x80000000u) { // radiance parked by an earlier stage
+                const float4 r0 = p.samples[idx];
+                rad = v3(r0.x, r0.y, r0.z);
+            }
+        }
+        HitRec h;
+        const uint32_t *list = nullptr;
+        uint32_t n_list = RT_LIST_OVERFLOW;
+        if (FIRST && p.lists != nullptr) { // the candidates of this path's pixel (camera rays only)
+            list = p.lists + (size_t)fast_div(idx, p.div_spp) * RT_LIST_WORDS;
+            n_list = list[0];
+            RT_DBG(n_list == RT_LIST_OVERFLOW || n_list < RT_LIST_WORDS, RT_DBG_LEAF);
+        }
+        if (FIRST && n_list != RT_LIST_OVERFLOW)
+            trace_candidates<COUNT, QUADS>(list + 1, n_list, sph, meta, quads, o, d, 0.001f, INFINITY, h, &wc);
+        else
+            trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
+                                           FIRST ? nullptr : chains, start);
+        n_rays++;
+        hit_slot = h.slot;
+        if (h.slot == RT_REF_NONE) {
+            rad = rad + thr * p.cam.background; // ray.go:53
+        } else {
+            n_hits++;
+            V3 atten, emitted;
+            bool scattered;
+            if (QUADS && (h.slot & RT_HIT_QUAD)) {
+                RT_DBG((h.slot & ~RT_HIT_QUAD) < RT_DBG_B(n_quad_slots), RT_DBG_HIT_SLOT);
+                const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
+                const uint32_t mi = __float_as_uint(q[1].w);
+                RT_DBG(mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
+                scattered = shade_hit_quad(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, q, h.t, rng, o, d, atten, emitted);
+            } else {
+                RT_DBG(h.slot < RT_DBG_B(n_slots), RT_DBG_HIT_SLOT);
+                const F4 s = sph[h.slot];
+                const int mi = meta[h.slot].y;
+                RT_DBG((uint32_t)mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
+                scattered = shade_hit(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, s, h.t, rng, o, d, atten, emitted);
+            }
+            rad = rad + thr * emitted; // ray.go:41,50
+            if (scattered) {
+                thr = thr * atten; // ray.go:48
+                survive = p.stage_depth + 1 < p.cam.max_depth; // ray.go:33-35
+            }
+        }
+        block = rng.block;
+        // no material of the reference both emits and scatters, so a survivor normally carries no
+        // radiance; if one ever does, it is parked in the sample slot and flagged in the queue entry
+        carries = survive && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f);
+        RT_DBG(idx < p.total_paths && idx < RT_DBG_B(samples_cap), RT_DBG_SAMPLE);
+        if (!survive || carries) p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
+    }
+    // append survivors, consecutive entries for consecutive lanes
+    const unsigned m = __ballot_sync(0xffffffffu, survive);
+    uint32_t first_entry = 0;
+    if constexpr (SMEM) { // one atomic per warp
+        if (m) {
+            if (lane == (unsigned)(__ffs(m) - 1)) first_entry = atomicAdd(p.queue_count, (unsigned)__popc(m));
+            first_entry = __shfl_sync(0xffffffffu, first_entry, __ffs(m) - 1);
+        }
+    } else {
+        // Scene in global memory (1 M spheres): one atomic per CTA and round, behind two barriers.  The
+        // barriers keep the CTA's warps on neighbouring pixels, which the L1-resident top of the tree likes
+        // (C4 +5.5 %); with the scene in shared memory they only add waiting (C2 -1 %), hence the split.
+        // The round count is the same for every thread of the grid, so the barriers are reached by all.
+        const unsigned warp = threadIdx.x >> 5;
+        if (lane == 0) cta_count[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        if (warp == 0) { // exclusive prefix over the warps' counts, then the CTA's reservation
+            const uint32_t c = lane < BLOCK / 32 ? cta_count[lane] : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int off = 1; off < BLOCK / 32; off <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((int)lane >= off) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, BLOCK / 32 - 1);
+            uint32_t base = 0;
+            if (lane == 0 && total) base = atomicAdd(p.queue_count, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < BLOCK / 32) cta_base[lane] = base + incl - c;
+        }
+        __syncthreads();
+        first_entry = cta_base[warp];
+    }
+    if (survive) {
+        const uint32_t e = first_entry + __popc(m & ((1u << lane) - 1u));
+        RT_DBG(e < p.total_paths && e < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
+        p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
+        p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block | (carries ? 0x80000000u : 0u)));
+        p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(hit_slot)); // the primitive the survivor leaves
+    }
+}
+
 template <int BLOCK, bool SMEM, bool COUNT, bool QUADS, bool FIRST = true>
 __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const F4 *nodes = p.sc.nodes, *sph = p.sc.sph, *mats = p.sc.mats, *quads = p.sc.quads;
-    const I2 *meta = p.sc.meta;
     typedef typename std::conditional<SMEM, StridedStack, LocalStack<RT_LOCAL_STACK>>::type Stack;
     Stack stack;
-    const uint32_t *chains = p.sc.chains, *sph_chain = p.sc.chains ? p.sc.sph_chain : nullptr, *quad_chain = p.sc.quad_chain;
-    if constexpr (SMEM) {
-        SmemScene s = stage_scene<RT_PACKED(SMEM, QUADS)>(p.sc, smem_raw);
-        nodes = s.nodes, sph = s.sph, mats = s.mats, quads = s.quads, meta = s.meta;
-        chains = s.chains, sph_chain = s.sph_chain, quad_chain = s.quad_chain;
-        stack.base = s.stack + threadIdx.x;
-        stack.stride = BLOCK;
-    }
-    const unsigned lane = threadIdx.x & 31u;
+    const SceneView sv = open_scene<SMEM, QUADS, Stack, BLOCK>(p.sc, smem_raw, stack);
     __shared__ uint32_t cta_count[BLOCK / 32], cta_base[BLOCK / 32];
     unsigned long long n_rays = 0, n_hits = 0;
     WorkCounters wc;
@@ -361,132 +504,10 @@ __global__ void __launch_bounds__(BLOCK) primary_stage_kernel(const __grid_const
     // whole warps iterate together (the trip count is warp-uniform), lanes past the end idle
     const uint32_t n_items = FIRST ? p.total_paths : *p.in_count;
     const uint32_t n_rounds = (n_items + BLOCK * gridDim.x - 1) / (BLOCK * gridDim.x);
-    for (uint32_t r = 0; r < n_rounds; r++) {
-        const uint32_t item = (r * gridDim.x + blockIdx.x) * BLOCK + threadIdx.x;
-        uint32_t idx = item;
-        bool survive = false, carries = false;
-        V3 o = v3(0, 0, 0), d = v3(0, 0, 0), thr = v3(1, 1, 1);
-        uint32_t block = 0, hit_slot = RT_REF_NONE;
-        if (item < n_items) {
-            PathRng rng;
-            V3 rad = v3(0, 0, 0);
-            uint32_t start = RT_REF_NONE;
-            if (FIRST) {
-                const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
-                const uint32_t pixel = image_pixel(p, p.pixel_begin + pp);
-                const int j = (int)fast_div(pixel, p.div_width), i = (int)(pixel - (uint32_t)j * p.cam.width);
-                rng.init(p.seed, pixel, p.sample_begin + k);
-                generate_ray(p.cam, rng, i, j, o, d);
-            } else {
-                RT_DBG(item < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
-                const float4 qo = p.in_o[item], qd = p.in_d[item], qt = p.in_t[item];
-                idx = __float_as_uint(qo.w);
-                const uint32_t pp = fast_div(idx, p.div_spp), k = idx - pp * p.spp_pass;
-                rng.init(p.seed, image_pixel(p, p.pixel_begin + pp), p.sample_begin + k);
-                rng.block = __float_as_uint(qd.w) & 0x7fffffffu;
-                o = v3(qo.x, qo.y, qo.z), d = v3(qd.x, qd.y, qd.z), thr = v3(qt.x, qt.y, qt.z);
-                start = chain_of_slot(sph_chain, quad_chain, __float_as_uint(qt.w));
-                if (__float_as_uint(qd.w) & 0x80000000u) { // radiance parked by an earlier stage
-                    const float4 r0 = p.samples[idx];
-                    rad = v3(r0.x, r0.y, r0.z);
-                }
-            }
-            HitRec h;
-            const uint32_t *list = nullptr;
-            uint32_t n_list = RT_LIST_OVERFLOW;
-            if (FIRST && p.lists != nullptr) { // the candidates of this path's pixel (camera rays only)
-                list = p.lists + (size_t)fast_div(idx, p.div_spp) * RT_LIST_WORDS;
-                n_list = list[0];
-                RT_DBG(n_list == RT_LIST_OVERFLOW || n_list < RT_LIST_WORDS, RT_DBG_LEAF);
-            }
-            if (FIRST && n_list != RT_LIST_OVERFLOW)
-                trace_candidates<COUNT, QUADS>(list + 1, n_list, sph, meta, quads, o, d, 0.001f, INFINITY, h, &wc);
-            else
-                trace_closest<Stack, COUNT, QUADS, false, SMEM ? RT_SMEM_NODE_STRIDE : 32, RT_PACKED(SMEM, QUADS)>(nodes, sph, meta, p.sc.root_ref, o, d, 0.001f, INFINITY, stack, h, &wc, quads,
-                                               FIRST ? nullptr : chains, start);
-            n_rays++;
-            hit_slot = h.slot;
-            if (h.slot == RT_REF_NONE) {
-                rad = rad + thr * p.cam.background; // ray.go:53
-            } else {
-                n_hits++;
-                V3 atten, emitted;
-                bool scattered;
-                if (QUADS && (h.slot & RT_HIT_QUAD)) {
-                    RT_DBG((h.slot & ~RT_HIT_QUAD) < RT_DBG_B(n_quad_slots), RT_DBG_HIT_SLOT);
-                    const F4 *q = quads + (size_t)RT_QUAD_F4 * (h.slot & ~RT_HIT_QUAD);
-                    const uint32_t mi = __float_as_uint(q[1].w);
-                    RT_DBG(mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
-                    scattered = shade_hit_quad(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, q, h.t, rng, o, d, atten, emitted);
-                } else {
-                    RT_DBG(h.slot < RT_DBG_B(n_slots), RT_DBG_HIT_SLOT);
-                    const F4 s = sph[h.slot];
-                    const int mi = meta[h.slot].y;
-                    RT_DBG((uint32_t)mi < RT_DBG_B(n_mats), RT_DBG_MATERIAL);
-                    scattered = shade_hit(mats[2 * mi], mats[2 * mi + 1], p.sc.tex, s, h.t, rng, o, d, atten, emitted);
-                }
-                rad = rad + thr * emitted; // ray.go:41,50
-                if (scattered) {
-                    thr = thr * atten; // ray.go:48
-                    survive = p.stage_depth + 1 < p.cam.max_depth; // ray.go:33-35
-                }
-            }
-            block = rng.block;
-            // no material of the reference both emits and scatters, so a survivor normally carries no
-            // radiance; if one ever does, it is parked in the sample slot and flagged in the queue entry
-            carries = survive && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f);
-            RT_DBG(idx < p.total_paths && idx < RT_DBG_B(samples_cap), RT_DBG_SAMPLE);
-            if (!survive || carries) p.samples[idx] = make_float4(rad.x, rad.y, rad.z, 0.0f);
-        }
-        // append survivors, consecutive entries for consecutive lanes
-        const unsigned m = __ballot_sync(0xffffffffu, survive);
-        uint32_t first_entry = 0;
-        if constexpr (SMEM) { // one atomic per warp
-            if (m) {
-                if (lane == (unsigned)(__ffs(m) - 1)) first_entry = atomicAdd(p.queue_count, (unsigned)__popc(m));
-                first_entry = __shfl_sync(0xffffffffu, first_entry, __ffs(m) - 1);
-            }
-        } else {
-            // Scene in global memory (1 M spheres): one atomic per CTA and round, behind two barriers.  The
-            // barriers keep the CTA's warps on neighbouring pixels, which the L1-resident top of the tree likes
-            // (C4 +5.5 %); with the scene in shared memory they only add waiting (C2 -1 %), hence the split.
-            // The round count is the same for every thread of the grid, so the barriers are reached by all.
-            const unsigned warp = threadIdx.x >> 5;
-            if (lane == 0) cta_count[warp] = (uint32_t)__popc(m);
-            __syncthreads();
-            if (warp == 0) { // exclusive prefix over the warps' counts, then the CTA's reservation
-                const uint32_t c = lane < BLOCK / 32 ? cta_count[lane] : 0u;
-                uint32_t incl = c;
-#pragma unroll
-                for (int off = 1; off < BLOCK / 32; off <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
-                    if ((int)lane >= off) incl += up;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, BLOCK / 32 - 1);
-                uint32_t base = 0;
-                if (lane == 0 && total) base = atomicAdd(p.queue_count, total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (lane < BLOCK / 32) cta_base[lane] = base + incl - c;
-            }
-            __syncthreads();
-            first_entry = cta_base[warp];
-        }
-        if (survive) {
-            const uint32_t e = first_entry + __popc(m & ((1u << lane) - 1u));
-            RT_DBG(e < p.total_paths && e < RT_DBG_B(queue_cap), RT_DBG_QUEUE);
-            p.queue_o[e] = make_float4(o.x, o.y, o.z, __uint_as_float(idx));
-            p.queue_d[e] = make_float4(d.x, d.y, d.z, __uint_as_float(block | (carries ? 0x80000000u : 0u)));
-            p.queue_t[e] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(hit_slot)); // the primitive the survivor leaves
-        }
-    }
-    unsigned long long v[4] = {n_rays, n_hits, wc.box_tests, wc.sphere_tests};
-#pragma unroll
-    for (int q = 0; q < (COUNT ? 4 : 2); q++) {
-        unsigned long long x = v[q];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0 && x) atomicAdd(p.stats + q, x);
-    }
+    for (uint32_t r = 0; r < n_rounds; r++)
+        primary_round<Stack, BLOCK, SMEM, COUNT, QUADS, FIRST>(p, sv, stack, (r * gridDim.x + blockIdx.x) * BLOCK + threadIdx.x, n_items,
+                                                               n_rays, n_hits, wc, cta_count, cta_base);
+    flush_counters<COUNT>(p.stats, n_rays, n_hits, wc);
 }
 
 // ---------------------------------------------------------------------------------------------
