@@ -172,7 +172,7 @@ typedef struct rt_camera_options {
 } rt_camera_options;
 
 typedef struct rt_render_opts {
-    uint64_t seed;         /* Philox4x32-10 key; the reference is clock-seeded (camera.go:170)    */
+    uint64_t seed;         /* Philox4x32-7 key; the reference is clock-seeded (camera.go:170)     */
     int32_t device;        /* CUDA ordinal                                                        */
     int32_t sample_offset; /* first global sample index rendered by this call (sample-split)      */
     int32_t sample_count;  /* samples per pixel rendered by this call; 0 = camera.spp             */
