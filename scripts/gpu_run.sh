@@ -14,7 +14,7 @@
 #   sweep:VAR:a,b,c bench-short once per value of environment variable VAR
 #   ab:NAME[:cfgs]  the default library against the variant build csrc/librt_b200_NAME.so
 #   ncu-launches    per-launch durations of the bench command (gpu__time_duration.sum)
-#   ncu-full[:SPP]  ncu --set full of one primary + one secondary launch at SPP (default 82) spp
+#   ncu-full[:SPP[:CFG]]  ncu --set full of one primary + one secondary launch at SPP (default 82) spp of config CFG (default C2)
 #   scale           bench.py at N = 1/2/4/8 under torchrun as the driver launches it, weak + strong
 #   multi           rt_render_multi on C2 / C5 in both split modes on all GPUs of the box
 set -u
@@ -81,7 +81,8 @@ for step in "$@"; do
       say "ncu-launches rc=$?" ;;
     ncu-full*)
       spp=$(echo "$step" | cut -s -d: -f2); [ -z "$spp" ] && spp=82
-      CMD="python bench.py --spp $spp --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-strong"
+      cfg=$(echo "$step" | cut -s -d: -f3); [ -z "$cfg" ] && cfg=C2
+      CMD="python bench.py --config $cfg --spp $spp --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-strong"
       $CMD > gpurun_out/${TAG}_plain_full.log 2>&1 && \
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_kernel|primary_stage" -s 2 -c 2 -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
       say "ncu-full rc=$?" ;;
