@@ -475,6 +475,8 @@ RT_HD uint32_t beam_candidates(const F4 *__restrict__ nodes, uint32_t root_ref, 
             if (n < cap) out[n] = s | flag;
             n++;
         }
+        if (n > cap) return n; // overflow: the caller falls back to the tree, no point in walking on (a beam along the
+                               // horizon of a million-sphere plane would otherwise visit thousands of leaves)
         ref = stack.pop();
     }
     return n;

@@ -124,3 +124,20 @@ def test_large_scene_through_render_multi(gpu, monkeypatch):
     srgb, sacc, sst = api.render_multi(scene, cam, devs, SEED, want_accum=True)
     assert sst.rays == st.rays and np.allclose(sacc, acc, rtol=2e-5, atol=1e-5)
     assert (np.abs(srgb.astype(int) - rgb.astype(int)) <= 1).all()
+
+
+def test_horizon_beams_overflow_their_lists_and_fall_back(gpu, monkeypatch):
+    """A camera low above a plane of 67 000 spheres: the beams of the pixels near the horizon touch far more leaves than
+    a candidate list holds; those pixels keep the tree traversal (the beam walk stops at the overflow).  With and without
+    the lists the frame is bit-identical."""
+    from tests import parity_report
+    scene = scenes.stress_scene(130)
+    cam = api.camera_from_options(scenes.camera_options(240, 16, **parity_report.FAR_CAMERA))
+    frames = []
+    for lists in ("1", "0"):
+        monkeypatch.setenv("RT_B200_PIXEL_LISTS", lists)
+        with api.Scene(scene) as sc:
+            frames.append(sc.render(cam, SEED, want_accum=True))
+    (rgb1, acc1, st1), (rgb0, acc0, st0) = frames
+    assert np.array_equal(acc1.view(np.uint32), acc0.view(np.uint32)) and np.array_equal(rgb1, rgb0) and st1.rays == st0.rays
+    assert st1.kernel_launches == st0.kernel_launches + 1 and st1.ms_render < 20 * st0.ms_render + 50
