@@ -176,6 +176,11 @@ __device__ __forceinline__ uint32_t image_pixel(const RenderParams &p, uint32_t 
     return (p.row_begin + jl * p.row_step) * w + (lp - jl * w);
 }
 
+#ifndef RT_GLOBAL_CTA_APPEND
+#define RT_GLOBAL_CTA_APPEND 1 /* global-memory scenes: survivors appended once per CTA and round (0: per warp, for A/B:
+                                   C4 1368 -> 1265 Msamples/s with the candidate lists, profiles/r02zo — the order of the
+                                   queue is what keeps the megakernel's warps on neighbouring parts of the tree) */
+#endif
 #define RT_CHUNK 256u /* path indices a warp claims per atomic */
 #define RT_LIST_WORDS 16u /* one 64-byte line per pixel: count + up to 15 candidate slots */
 #define RT_LIST_OVERFLOW 0xFFFFFFFFu
@@ -452,7 +457,7 @@ __device__ __forceinline__ void primary_round(const RenderParams &p, const Scene
     // append survivors, consecutive entries for consecutive lanes
     const unsigned m = __ballot_sync(0xffffffffu, survive);
     uint32_t first_entry = 0;
-    if constexpr (SMEM) { // one atomic per warp
+    if constexpr (SMEM || !RT_GLOBAL_CTA_APPEND) { // one atomic per warp
         if (m) {
             if (lane == (unsigned)(__ffs(m) - 1)) first_entry = atomicAdd(p.queue_count, (unsigned)__popc(m));
             first_entry = __shfl_sync(0xffffffffu, first_entry, __ffs(m) - 1);
