@@ -946,6 +946,7 @@ static int render_accum(rt_scene *s, const rt_camera *cam, const rt_render_opts 
     p.cam = make_dev_camera(*cam);
     p.seed = opts->seed;
     p.row_begin = (uint32_t)rows.begin, p.row_step = (uint32_t)rows.step;
+    p.div_width = fast_div_magic((uint32_t)cam->width), p.div_spp = 0; // (image_pixel needs div_width: also in the candidate walk)
     p.samples = ws.samples;
     p.counter = s->d_counter;
     p.stats = s->d_stats;
