@@ -373,7 +373,7 @@ def main():
     # scene handle built WITHOUT the leaf-start chains and rendered WITHOUT the per-pixel candidate lists; what today's
     # kernels execute (fewer box tests: leaf start skips the ancestors of the leaf a ray leaves, camera rays test their
     # pixel's candidate list instead of walking the tree) is reported next to it as `executed`. ----
-    cnt_spp = max(1, min(spp, 4))
+    cnt_spp = max(1, min(spp, 16))  # (16: the candidate lists are built from 16 spp on, so the count sees what the run executes)
 
     def count_work(scene_handle):
         stc = scene_handle.render_accum_device(cam, accum.data_ptr(), scenes.RENDER_SEED, sample_offset=0,
