@@ -524,3 +524,48 @@ extern "C" int hs_pixel_candidates(const rt_scene_desc *d, const rt_camera *cam,
     }
     return 0;
 }
+
+// Property behind the candidate lists, at the level of ONE box: whenever the kernels' slab test (box_test) accepts a
+// ray drawn from a beam, the beam test (beam_box_test) accepts the box.  Random boxes (incl. flat and huge ones), random
+// beams (origin box x direction box, narrow like a pixel's or wide, some straddling zero on an axis), `rays` rays per
+// beam.  Returns the number of violations; *accepted = (box, beam) pairs in which at least one ray was accepted.
+extern "C" int64_t hs_beam_box_property(uint64_t seed, int64_t n_pairs, int rays, int64_t *accepted) {
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { // xorshift64*, uniform in [0, 1)
+        st ^= st >> 12, st ^= st << 25, st ^= st >> 27;
+        return (float)((st * 0x2545F4914F6CDD1Dull) >> 40) * (1.0f / 16777216.0f);
+    };
+    auto sym = [&](float s) { return (rnd() * 2 - 1) * s; };
+    int64_t bad = 0, acc = 0;
+    for (int64_t k = 0; k < n_pairs; k++) {
+        const float scale = powf(10.0f, sym(2.0f));
+        F4 c = {sym(20) * scale, sym(20) * scale, sym(20) * scale, 0}, h = {rnd() * 3 * scale, rnd() * 3 * scale, rnd() * 3 * scale, 0};
+        if (k % 7 == 0) h.y = 0;                 // flat box
+        if (k % 11 == 0) h.x = h.z = 1000 * scale; // the ground
+        Beam b;
+        const V3 o = v3(sym(30) * scale, sym(30) * scale, sym(30) * scale);
+        const float ow = (k % 3 == 0) ? 0.0f : rnd() * 0.1f * scale;
+        V3 d = v3(c.x - o.x + sym(2) * h.x, c.y - o.y + sym(2) * h.y, c.z - o.z + sym(2) * h.z); // aimed near the box
+        if (k % 5 == 0) d = v3(sym(1), sym(1), sym(1));
+        const float dw = (k % 4 == 0 ? 0.5f : 0.002f) * (fabsf(d.x) + fabsf(d.y) + fabsf(d.z)) * rnd();
+        b.olo = v3(o.x - ow, o.y - ow, o.z - ow), b.ohi = v3(o.x + ow, o.y + ow, o.z + ow);
+        b.dlo = v3(d.x - dw, d.y - dw, d.z - dw), b.dhi = v3(d.x + dw, d.y + dw, d.z + dw);
+        const bool beam_hit = beam_box_test(c, h, b);
+        bool any = false;
+        for (int r = 0; r < rays; r++) {
+            const V3 ro = v3(b.olo.x + rnd() * (b.ohi.x - b.olo.x), b.olo.y + rnd() * (b.ohi.y - b.olo.y), b.olo.z + rnd() * (b.ohi.z - b.olo.z));
+            V3 rd = v3(b.dlo.x + rnd() * (b.dhi.x - b.dlo.x), b.dlo.y + rnd() * (b.dhi.y - b.dlo.y), b.dlo.z + rnd() * (b.dhi.z - b.dlo.z));
+            if (r == 0) rd = b.dlo; // corners too
+            if (r == 1) rd = b.dhi;
+            const V3 inv = v3(cull_rcp(rd.x), cull_rcp(rd.y), cull_rcp(rd.z));
+            const V3 noi = v3(-(ro.x * inv.x), -(ro.y * inv.y), -(ro.z * inv.z));
+            const V3 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
+            float tn;
+            if (box_test(c, h, inv, noi, ainv, 0.001f, INFINITY, tn)) any = true;
+        }
+        if (any) acc++;
+        if (any && !beam_hit) bad++;
+    }
+    if (accepted) *accepted = acc;
+    return bad;
+}

@@ -415,3 +415,16 @@ def test_pixel_candidate_lists_are_supersets(hs, name):
     assert r["pixels"] == n and r["missing"] == 0 and r["differ"] == 0
     if name == "random":
         assert 3.5 < r["mean"] < 6.0 and r["longest"] <= 24 and r["overflow"] < 0.01 * n
+
+
+def test_beam_test_is_conservative_for_single_boxes(hs):
+    """The property the candidate lists rest on, one box at a time: if the kernels' slab test accepts ANY ray drawn from a
+    beam, the beam test accepts the box.  800 000 random (box, beam) pairs — flat boxes, the huge ground box, beams as
+    narrow as a pixel's and wide ones, direction intervals that straddle zero — 24 rays each, corners included."""
+    hs.hs_beam_box_property.restype = C.c_int64
+    total = 0
+    for seed in range(4):
+        acc = C.c_int64()
+        assert hs.hs_beam_box_property(C.c_uint64(seed), C.c_int64(200_000), 24, C.byref(acc)) == 0
+        total += acc.value
+    assert total > 200_000          # the rays do hit their boxes in a third of the pairs: the property is exercised
